@@ -1,0 +1,185 @@
+/* psp_b200.h -- C-ABI of libpsp_b200.so, the B200 (sm_100a) implementation of
+ * PySparse's data-parallel hot path: fp64 CSR / SSS SpMV, the six Krylov
+ * solvers and the Jacobi / SSOR preconditioners.
+ *
+ * This is the drop-in boundary.  Every entry point is `extern "C"`, takes
+ * plain pointers and sizes, and replaces one interface of the reference
+ * (cited as file:line under /root/reference/).  The CPython glue in
+ * pysparse_b200/host/ (modules spmatrix, krylov, precon) is a thin caller of
+ * these functions; INTEGRATION.md shows the binding a PySparse maintainer
+ * would add to the reference's own C sources.
+ *
+ * Conventions
+ *  - indices are 32-bit C int, 0-based; values are IEEE fp64;
+ *  - every function returns PSP_OK (0) or a negative psp_status; the message
+ *    of the last failure is available from psp_last_error();
+ *  - "host" pointers are ordinary (pageable or pinned) CPU memory, "dev"
+ *    pointers come from psp_vec_alloc();
+ *  - there is NO CPU fallback: without a CUDA device every compute call
+ *    fails with PSP_ERR_NO_DEVICE.
+ */
+#ifndef PSP_B200_H
+#define PSP_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum psp_status {
+  PSP_OK = 0,
+  PSP_ERR_NO_DEVICE = -1,   /* no usable CUDA device / driver            */
+  PSP_ERR_CUDA = -2,        /* a CUDA runtime call failed                 */
+  PSP_ERR_ARG = -3,         /* invalid argument (shape, NULL, ...)        */
+  PSP_ERR_NOMEM = -4,       /* host or device allocation failed           */
+  PSP_ERR_CALLBACK = -5,    /* a foreign operator callback reported -1    */
+  PSP_ERR_STRUCTURE = -6,   /* matrix structure invalid (unsorted, range) */
+  PSP_ERR_DIST = -7         /* multi-GPU layer (NCCL / peer access) error */
+} psp_status;
+
+typedef struct psp_mat psp_mat;     /* device-resident sparse matrix        */
+typedef struct psp_prec psp_prec;   /* device-resident preconditioner       */
+
+/* ---- runtime ---------------------------------------------------------- */
+
+/* Select the CUDA device and create the context (streams, scratch).  Called
+ * implicitly (device 0, or $PSP_DEVICE) by the first compute call. */
+int psp_init(int device);
+int psp_device_count(void);             /* 0 when there is no GPU/driver     */
+int psp_current_device(void);           /* -1 before psp_init                */
+const char *psp_last_error(void);
+const char *psp_version(void);
+/* number of kernels this library has launched since the last reset (the
+ * `gpu_launches` figure of bench.py) */
+long long psp_launch_count(int reset);
+int psp_synchronize(void);
+
+/* pinned host memory for fast host<->device staging (optional) */
+int psp_host_alloc(size_t bytes, void **out);
+int psp_host_free(void *p);
+
+/* ---- matrices --------------------------------------------------------- */
+
+/* CSR matrix: replaces CSRMatObject (pysparse/include/csr_mat.h:6-13) as
+ * produced by ll_mat.to_csr() (pysparse/sparse/src/ll_mat.c:1577-1648).
+ * ind[m+1], col[nnz], val[nnz]; arrays are copied to the device. */
+int psp_csr_create(int m, int n, int nnz, const int *ind, const int *col,
+                   const double *val, psp_mat **out);
+
+/* SSS matrix (strict lower triangle in CSR + dense diagonal): replaces
+ * SSSMatObject (pysparse/include/sss_mat.h:6-14) as produced by
+ * ll_mat.to_sss() (ll_mat.c:1654-1708).  The one-time transpose index that
+ * makes the upper-triangle part an atomic-free gather is built here. */
+int psp_sss_create(int n, int nnz, const int *ind, const int *col,
+                   const double *val, const double *diag, psp_mat **out);
+
+void psp_mat_destroy(psp_mat *a);
+/* kind: 1 = CSR, 2 = SSS */
+int psp_mat_info(const psp_mat *a, int *m, int *n, long long *nnz, int *kind);
+
+/* y := A x (transp = 0) or y := A^T x (transp != 0) with HOST vectors and
+ * element strides incx / incy: replaces csr_matvec_kernel(_stride) /
+ * csr_matvec_transp_kernel(_stride) (csr_mat.c:17-106) and sss_matvec(_stride)
+ * (sss_mat.c:40-76) behind CSRMat_matvec / SSSMat_matvec. */
+int psp_matvec(psp_mat *a, int transp, const double *x, long incx, double *y, long incy);
+
+/* same with DEVICE vectors (contiguous); asynchronous on the library stream */
+int psp_matvec_dev(psp_mat *a, int transp, const double *dx, double *dy);
+
+/* ---- device vectors (used by benchmarks and the callback path) -------- */
+int psp_vec_alloc(size_t n, double **dptr);
+int psp_vec_free(double *dptr);
+int psp_vec_upload(double *dptr, const double *host, size_t n, long inc);
+int psp_vec_download(const double *dptr, double *host, size_t n, long inc);
+int psp_vec_fill(double *dptr, size_t n, double value);
+
+/* ---- preconditioners --------------------------------------------------- */
+
+/* Jacobi: replaces newJacobiObject + jacobi() (pysparse/precon/src/
+ * preconmodule.c:352-412, :35-54).  diag[n] are the matrix diagonal entries
+ * A[i,i]; dinv = omega/diag is formed here; PSP_ERR_ARG with the reference's
+ * message "diagonal element close to zero" when 1.0 + d == 1.0.  `a` is only
+ * needed (and may otherwise be NULL) for steps > 1. */
+int psp_jacobi_create(psp_mat *a, int n, const double *diag, double omega, int steps,
+                      psp_prec **out);
+
+/* SSOR / symmetric Gauss-Seidel: replaces newSSORObject + ssor_kernel /
+ * symgs_kernel (preconmodule.c:414-459, :95-193).  `sss` must be an SSS
+ * matrix.  Runs the level-set analysis of L (forward sweep) and L^T (backward
+ * sweep); the sweeps keep the reference's lexicographic dependency order. */
+int psp_ssor_create(psp_mat *sss, double omega, int steps, psp_prec **out);
+
+void psp_prec_destroy(psp_prec *k);
+
+/* y := K^-1 x with HOST vectors (contiguous): Jacobi_precon / SSOR_precon
+ * (preconmodule.c:60-80, :199-223) */
+int psp_prec_apply(psp_prec *k, const double *x, double *y);
+int psp_prec_apply_dev(psp_prec *k, const double *dx, double *dy);
+
+/* level-set structure of an SSOR preconditioner (bit-exact integer work;
+ * exposed for the parity tests): number of forward / backward levels and,
+ * optionally, the level of every row (arrays of n ints, may be NULL). */
+int psp_ssor_levels(const psp_prec *k, int *nlev_fwd, int *nlev_bwd,
+                    int *level_fwd, int *level_bwd);
+
+/* ---- Krylov solvers ---------------------------------------------------- */
+
+typedef enum psp_solver {
+  PSP_PCG = 0,       /* Itsolvers_pcg_kernel      pysparse/itsolvers/src/pcg.c:22-171      */
+  PSP_MINRES = 1,    /* Itsolvers_minres_kernel   .../minres.c:43-200                      */
+  PSP_QMRS = 2,      /* Itsolvers_qmrs_kernel     .../qmrs.c:34-154                        */
+  PSP_BICGSTAB = 3,  /* Itsolvers_bicgstab_kernel .../bicgstab.c:182-300                   */
+  PSP_CGS = 4,       /* Itsolvers_cgs_kernel      .../cgs.c:13-111                         */
+  PSP_GMRES = 5      /* Itsolvers_gmres_kernel    .../gmres.c:73-206                       */
+} psp_solver;
+
+/* A foreign (duck-typed) operator: y := Op(x) on HOST buffers of length n.
+ * Return 0 on success, non-zero on failure (mirrors SpMatrix_Matvec /
+ * SpMatrix_Precon, pysparse/sparse/src/spmatrixmodule.c:169-248). */
+typedef int (*psp_callback)(void *ctx, int n, const double *x, double *y);
+
+/* An operator is EITHER a native handle (solve stays on the device) OR a
+ * callback (vectors are staged through host memory around each call). */
+typedef struct psp_operator {
+  psp_mat *mat;        /* native matrix, or NULL                      */
+  psp_prec *prec;      /* native preconditioner, or NULL              */
+  psp_callback cb;     /* foreign operator, used when both are NULL   */
+  void *ctx;
+} psp_operator;
+
+/* Solve A x = b.  Replaces the six wrappers ItSolvers_<solver>
+ * (pysparse/itsolvers/src/itsolversmodule.c:32-586) together with the
+ * kernels they call: same start vector convention (x is the initial guess,
+ * except QMRS which ignores it), same stopping rules, same
+ * (info, iter, relres) results including the reference's quirks
+ * (PCG iter = maxit+1 on non-convergence, 0-based CGS count, GMRES info
+ * always 0 ...).  b and x are HOST arrays of length n; x is overwritten.
+ * K may be NULL (no preconditioner).  gmres_dim is only read for PSP_GMRES.
+ * Where the reference leaves relres uninitialised (MINRES / BiCGSTAB
+ * breakdown) NaN is returned. */
+int psp_solve(int solver, const psp_operator *A, const psp_operator *K, int n,
+              const double *b, double *x, double tol, int maxit, int gmres_dim,
+              int *info, int *iter, double *relres);
+
+/* Same, with b and x resident on the device (no host<->device vector
+ * traffic); used to time the solve with inputs already in HBM. */
+int psp_solve_dev(int solver, const psp_operator *A, const psp_operator *K, int n,
+                  const double *db, double *dx, double tol, int maxit, int gmres_dim,
+                  int *info, int *iter, double *relres);
+
+/* Time of the device part of the most recent psp_solve / psp_solve_dev /
+ * psp_matvec call, measured with CUDA events on the library stream (ms). */
+double psp_last_device_ms(void);
+
+/* ---- tuning knobs (default to reference semantics) --------------------- */
+/* name: "spmv_variant" (0 auto, 1 scalar-stream, 2 vector-stream ...),
+ *       "poll_chunk" (iterations enqueued between convergence polls),
+ *       "use_graph" (capture iteration bodies in CUDA graphs)              */
+int psp_set_option(const char *name, long long value);
+long long psp_get_option(const char *name);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSP_B200_H */

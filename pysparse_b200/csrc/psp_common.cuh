@@ -1,0 +1,195 @@
+// psp_common.cuh -- shared internals of libpsp_b200.so (context, error handling,
+// deterministic reductions, the device-side solver state).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "psp_b200.h"
+
+namespace psp {
+
+// ---------------------------------------------------------------- errors
+void set_error(const char *fmt, ...);
+
+#define PSP_CUDA(call)                                                              \
+  do {                                                                              \
+    cudaError_t e_ = (call);                                                        \
+    if (e_ != cudaSuccess) {                                                        \
+      psp::set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__,           \
+                     cudaGetErrorString(e_));                                       \
+      return PSP_ERR_CUDA;                                                          \
+    }                                                                               \
+  } while (0)
+
+#define PSP_TRY(call)                 \
+  do {                                \
+    int s_ = (call);                  \
+    if (s_ != PSP_OK) return s_;      \
+  } while (0)
+
+// ---------------------------------------------------------------- context
+constexpr int kMaxGrid = 148 * 16;  // upper bound on persistent grid sizes
+constexpr int kRedSlots = 8;        // sums a single kernel may reduce
+constexpr int kThreads = 256;
+
+// Device-side solver state.  One instance lives in device memory for the
+// duration of a solve; every kernel of the solve reads `done` first and
+// returns immediately when it is set, so iterations enqueued past the point
+// of convergence cost a few microseconds and change nothing.
+struct State {
+  int done;      // 1: solve finished, remaining kernels are no-ops
+  int info;      // solver flag / info as the reference reports it
+  int iter;      // iteration count as the reference reports it
+  int it;        // running iteration counter
+  int maxit;
+  int stag;      // PCG stagnation latch
+  int inner;     // GMRES: index inside the restart cycle
+  int phase;     // solver-specific phase latch
+  int mdim;      // GMRES restart length
+  int cyc_done;  // GMRES: inner loop of the current cycle finished
+  int last_i;    // GMRES: last inner index of the cycle
+  int pad0;
+  double tol;
+  double relres;
+  double red[kRedSlots];   // raw results of the last reduction
+  double redmax;           // raw result of the last max-reduction
+  double v[48];            // solver scalars (alpha, beta, rho, ...)
+};
+
+struct Ctx {
+  bool ready = false;
+  int device = -1;
+  int sms = 0;
+  cudaStream_t stream = nullptr;
+  double *partials = nullptr;       // [kRedSlots+1][kMaxGrid]
+  unsigned *tickets = nullptr;      // [16] zero-initialised ticket counters
+  State *state = nullptr;           // device solver state
+  State *h_state = nullptr;         // pinned mirror
+  double *stage = nullptr;          // pinned staging for strided / small copies
+  size_t stage_elems = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evpoll[2] = {nullptr, nullptr};
+  double last_ms = 0.0;
+  long long launches = 0;
+  // options
+  long long spmv_variant = 0;
+  long long poll_chunk = 0;   // 0: automatic
+  long long use_graph = 1;
+};
+
+Ctx &ctx();
+int ensure_init();                   // PSP_OK or error; lazily initialises device 0
+int ensure_stage(size_t elems);      // pinned staging buffer of at least `elems` doubles
+
+inline int grid_for(size_t work_items, int per_sm = 8) {
+  Ctx &c = ctx();
+  long long g = (long long)((work_items + kThreads - 1) / kThreads);
+  long long cap = (long long)c.sms * per_sm;
+  if (cap > kMaxGrid) cap = kMaxGrid;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+#define PSP_LAUNCH_CHECK()                                                        \
+  do {                                                                            \
+    psp::ctx().launches++;                                                        \
+    cudaError_t e_ = cudaGetLastError();                                          \
+    if (e_ != cudaSuccess) {                                                      \
+      psp::set_error("kernel launch failed at %s:%d: %s", __FILE__, __LINE__,     \
+                     cudaGetErrorString(e_));                                     \
+      return PSP_ERR_CUDA;                                                        \
+    }                                                                             \
+  } while (0)
+
+// ---------------------------------------------------------------- device helpers
+#ifdef __CUDACC__
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Deterministic block-wide sum for blockDim.x == kThreads (8 warps).  Result
+// valid in thread 0.  `sh` must hold 8 doubles; contains a __syncthreads().
+__device__ __forceinline__ double block_sum(double v, double *sh) {
+  v = warp_sum(v);
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (w == 0) {
+    r = (l < (blockDim.x >> 5)) ? sh[l] : 0.0;
+    r = warp_sum(r);
+  }
+  return r;
+}
+
+__device__ __forceinline__ double block_max(double v, double *sh) {
+  v = warp_max(v);
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (w == 0) {
+    r = (l < (blockDim.x >> 5)) ? sh[l] : 0.0;
+    r = warp_max(r);
+  }
+  return r;
+}
+
+// Second stage of a grid-wide deterministic reduction.  Every block has put
+// its NS partial sums (and optionally one partial max) into
+// partials[s * kMaxGrid + blockIdx.x]; the block that draws the last ticket
+// adds them up in a fixed order (independent of which block that is) and
+// returns true in ALL its threads with totals[] valid in thread 0.
+template <int NS, bool HASMAX>
+__device__ __forceinline__ bool grid_reduce_finish(const double *mine, double mymax,
+                                                   double *partials, unsigned *ticket,
+                                                   double *totals, double *totmax, double *sh) {
+  __shared__ bool is_last;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < NS; s++) partials[s * kMaxGrid + blockIdx.x] = mine[s];
+    if (HASMAX) partials[kRedSlots * kMaxGrid + blockIdx.x] = mymax;
+    __threadfence();
+    unsigned t = atomicAdd(ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return false;
+  __threadfence();
+  const volatile double *vp = partials;
+#pragma unroll
+  for (int s = 0; s < NS; s++) {
+    double a = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) a += vp[s * kMaxGrid + i];
+    a = block_sum(a, sh);
+    if (threadIdx.x == 0) totals[s] = a;
+  }
+  if (HASMAX) {
+    double a = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x)
+      a = fmax(a, vp[kRedSlots * kMaxGrid + i]);
+    a = block_max(a, sh);
+    if (threadIdx.x == 0) *totmax = a;
+  }
+  if (threadIdx.x == 0) *ticket = 0u;  // re-arm for the next kernel (stream-ordered)
+  return true;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace psp

@@ -1,0 +1,201 @@
+// psp_runtime.cu -- context, error reporting, device vectors, options.
+#include "psp_common.cuh"
+
+namespace psp {
+
+static thread_local char g_err[512] = "";
+static Ctx g_ctx;
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+}
+
+Ctx &ctx() { return g_ctx; }
+
+static int do_init(int device) {
+  Ctx &c = g_ctx;
+  if (c.ready && c.device == device) return PSP_OK;
+  if (c.ready) { set_error("psp_init: already initialised on device %d", c.device); return PSP_ERR_ARG; }
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    set_error("no CUDA device available (%s); pysparse_b200 has no CPU fallback",
+              e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    cudaGetLastError();
+    return PSP_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= count) { set_error("psp_init: device %d out of range (%d devices)", device, count); return PSP_ERR_ARG; }
+  PSP_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  PSP_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) {
+    set_error("device %d (%s, sm_%d%d) is not a Blackwell sm_100 part; this library ships sm_100a code only",
+              device, prop.name, prop.major, prop.minor);
+    return PSP_ERR_NO_DEVICE;
+  }
+  c.device = device;
+  c.sms = prop.multiProcessorCount;
+  PSP_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  PSP_CUDA(cudaMalloc((void **)&c.partials, sizeof(double) * (kRedSlots + 1) * kMaxGrid));
+  PSP_CUDA(cudaMalloc((void **)&c.tickets, sizeof(unsigned) * 16));
+  PSP_CUDA(cudaMemset(c.tickets, 0, sizeof(unsigned) * 16));
+  PSP_CUDA(cudaMalloc((void **)&c.state, sizeof(State) + 256));
+  PSP_CUDA(cudaMemset(c.state, 0, sizeof(State) + 256));
+  PSP_CUDA(cudaHostAlloc((void **)&c.h_state, 2 * sizeof(State), cudaHostAllocDefault));
+  PSP_CUDA(cudaEventCreate(&c.ev0));
+  PSP_CUDA(cudaEventCreate(&c.ev1));
+  PSP_CUDA(cudaEventCreateWithFlags(&c.evpoll[0], cudaEventDisableTiming));
+  PSP_CUDA(cudaEventCreateWithFlags(&c.evpoll[1], cudaEventDisableTiming));
+  c.ready = true;
+  return PSP_OK;
+}
+
+int ensure_init() {
+  if (g_ctx.ready) {
+    cudaSetDevice(g_ctx.device);
+    return PSP_OK;
+  }
+  int dev = 0;
+  if (const char *s = getenv("PSP_DEVICE")) dev = atoi(s);
+  else if (const char *s2 = getenv("LOCAL_RANK")) dev = atoi(s2);
+  return do_init(dev);
+}
+
+int ensure_stage(size_t elems) {
+  Ctx &c = g_ctx;
+  if (c.stage_elems >= elems) return PSP_OK;
+  if (c.stage) cudaFreeHost(c.stage);
+  c.stage = nullptr; c.stage_elems = 0;
+  size_t want = elems < (1u << 16) ? (1u << 16) : elems;
+  cudaError_t e = cudaHostAlloc((void **)&c.stage, sizeof(double) * want, cudaHostAllocDefault);
+  if (e != cudaSuccess) { set_error("cudaHostAlloc(%zu doubles) failed: %s", want, cudaGetErrorString(e)); return PSP_ERR_NOMEM; }
+  c.stage_elems = want;
+  return PSP_OK;
+}
+
+__global__ void k_fill(double *p, size_t n, double v) {
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
+}
+
+}  // namespace psp
+
+using namespace psp;
+
+extern "C" int psp_init(int device) { return do_init(device); }
+
+extern "C" int psp_device_count(void) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return count;
+}
+
+extern "C" int psp_current_device(void) { return g_ctx.ready ? g_ctx.device : -1; }
+extern "C" const char *psp_last_error(void) { return g_err; }
+extern "C" const char *psp_version(void) { return "pysparse_b200 0.1.0 (sm_100a)"; }
+
+extern "C" long long psp_launch_count(int reset) {
+  long long v = g_ctx.launches;
+  if (reset) g_ctx.launches = 0;
+  return v;
+}
+
+extern "C" int psp_synchronize(void) {
+  PSP_TRY(ensure_init());
+  PSP_CUDA(cudaStreamSynchronize(g_ctx.stream));
+  return PSP_OK;
+}
+
+extern "C" double psp_last_device_ms(void) { return g_ctx.last_ms; }
+
+extern "C" int psp_host_alloc(size_t bytes, void **out) {
+  if (!out) { set_error("psp_host_alloc: NULL out"); return PSP_ERR_ARG; }
+  PSP_TRY(ensure_init());
+  cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+  if (e != cudaSuccess) { set_error("cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); return PSP_ERR_NOMEM; }
+  return PSP_OK;
+}
+
+extern "C" int psp_host_free(void *p) {
+  if (p) PSP_CUDA(cudaFreeHost(p));
+  return PSP_OK;
+}
+
+extern "C" int psp_vec_alloc(size_t n, double **dptr) {
+  if (!dptr) { set_error("psp_vec_alloc: NULL out"); return PSP_ERR_ARG; }
+  PSP_TRY(ensure_init());
+  cudaError_t e = cudaMalloc((void **)dptr, sizeof(double) * (n ? n : 1));
+  if (e != cudaSuccess) { set_error("cudaMalloc(%zu doubles) failed: %s", n, cudaGetErrorString(e)); return PSP_ERR_NOMEM; }
+  return PSP_OK;
+}
+
+extern "C" int psp_vec_free(double *dptr) {
+  if (dptr) PSP_CUDA(cudaFree(dptr));
+  return PSP_OK;
+}
+
+// host -> device, element stride `inc` on the host side (NumPy strided views)
+extern "C" int psp_vec_upload(double *dptr, const double *host, size_t n, long inc) {
+  if (n == 0) return PSP_OK;
+  if (!dptr || !host) { set_error("psp_vec_upload: NULL argument"); return PSP_ERR_ARG; }
+  PSP_TRY(ensure_init());
+  Ctx &c = g_ctx;
+  if (inc == 1) {
+    PSP_CUDA(cudaMemcpyAsync(dptr, host, sizeof(double) * n, cudaMemcpyHostToDevice, c.stream));
+    PSP_CUDA(cudaStreamSynchronize(c.stream));
+    return PSP_OK;
+  }
+  PSP_TRY(ensure_stage(n));
+  for (size_t i = 0; i < n; i++) c.stage[i] = host[(long)i * inc];
+  PSP_CUDA(cudaMemcpyAsync(dptr, c.stage, sizeof(double) * n, cudaMemcpyHostToDevice, c.stream));
+  PSP_CUDA(cudaStreamSynchronize(c.stream));
+  return PSP_OK;
+}
+
+extern "C" int psp_vec_download(const double *dptr, double *host, size_t n, long inc) {
+  if (n == 0) return PSP_OK;
+  if (!dptr || !host) { set_error("psp_vec_download: NULL argument"); return PSP_ERR_ARG; }
+  PSP_TRY(ensure_init());
+  Ctx &c = g_ctx;
+  if (inc == 1) {
+    PSP_CUDA(cudaMemcpyAsync(host, dptr, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
+    PSP_CUDA(cudaStreamSynchronize(c.stream));
+    return PSP_OK;
+  }
+  PSP_TRY(ensure_stage(n));
+  PSP_CUDA(cudaMemcpyAsync(c.stage, dptr, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
+  PSP_CUDA(cudaStreamSynchronize(c.stream));
+  for (size_t i = 0; i < n; i++) host[(long)i * inc] = c.stage[i];
+  return PSP_OK;
+}
+
+extern "C" int psp_vec_fill(double *dptr, size_t n, double value) {
+  if (n == 0) return PSP_OK;
+  PSP_TRY(ensure_init());
+  k_fill<<<grid_for(n), kThreads, 0, g_ctx.stream>>>(dptr, n, value);
+  PSP_LAUNCH_CHECK();
+  return PSP_OK;
+}
+
+extern "C" int psp_set_option(const char *name, long long value) {
+  if (!name) return PSP_ERR_ARG;
+  Ctx &c = g_ctx;
+  if (!strcmp(name, "spmv_variant")) c.spmv_variant = value;
+  else if (!strcmp(name, "poll_chunk")) c.poll_chunk = value;
+  else if (!strcmp(name, "use_graph")) c.use_graph = value;
+  else { set_error("unknown option '%s'", name); return PSP_ERR_ARG; }
+  return PSP_OK;
+}
+
+extern "C" long long psp_get_option(const char *name) {
+  Ctx &c = g_ctx;
+  if (!name) return -1;
+  if (!strcmp(name, "spmv_variant")) return c.spmv_variant;
+  if (!strcmp(name, "poll_chunk")) return c.poll_chunk;
+  if (!strcmp(name, "use_graph")) return c.use_graph;
+  if (!strcmp(name, "sms")) return c.sms;
+  return -1;
+}

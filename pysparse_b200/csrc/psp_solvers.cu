@@ -1,0 +1,797 @@
+// psp_solvers.cu -- the six Krylov solvers, device-resident.
+//
+// Replaces Itsolvers_{pcg,minres,qmrs,bicgstab,cgs,gmres}_kernel
+// (pysparse/itsolvers/src/*.c) and their Python wrappers' workspace handling
+// (itsolversmodule.c:32-586).  Vectors stay in HBM for the whole solve; every
+// iteration is a short, fixed sequence of fused kernels (psp_vec.cuh,
+// psp_spmv.cu) whose scalar work runs in device-side epilogues
+// (psp_epilogue.cuh).  The host enqueues iterations ahead of the GPU and only
+// polls the `done` flag asynchronously, so there is no host synchronisation
+// per step.  Foreign (Python) operators are supported by staging the operand
+// vectors through pinned host memory around each callback.
+#include "psp_mat.cuh"
+#include "psp_vec.cuh"
+
+namespace psp {
+
+int prec_apply_dev(psp_prec *K, const double *dx, double *dy, State *gateS);   // psp_precon.cu
+
+// ------------------------------------------------------------------ generic functors
+struct FNormSq {            // red0 = sum a_i^2
+  static constexpr int NS = 1; static constexpr bool HASMAX = false, TICKET = false;
+  const double *a;
+  __device__ void prepare(const State *) {}
+  __device__ void elem(long i, double *acc, double &) { double t = a[i]; acc[0] += t * t; }
+};
+struct FDot {               // red0 = sum a_i b_i
+  static constexpr int NS = 1; static constexpr bool HASMAX = false, TICKET = false;
+  const double *a, *b;
+  __device__ void prepare(const State *) {}
+  __device__ void elem(long i, double *acc, double &) { acc[0] += a[i] * b[i]; }
+};
+struct FDots2 {             // red0 = sum w1_i y_i ; red1 = sum w2_i y_i (w2 may be y)
+  static constexpr int NS = 2; static constexpr bool HASMAX = false, TICKET = false;
+  const double *w1, *w2, *y;
+  __device__ void prepare(const State *) {}
+  __device__ void elem(long i, double *acc, double &) {
+    double t = y[i];
+    if (w1) acc[0] += w1[i] * t;
+    if (w2) acc[1] += w2[i] * t;
+  }
+};
+struct FCopy {
+  static constexpr int NS = 0; static constexpr bool HASMAX = false, TICKET = false;
+  const double *a; double *b;
+  __device__ void prepare(const State *) {}
+  __device__ void elem(long i, double *, double &) { b[i] = a[i]; }
+};
+
+struct FScaleBy {           // y = x .* dinv
+  static constexpr int NS = 0; static constexpr bool HASMAX = false, TICKET = false;
+  const double *x, *dinv; double *y;
+  __device__ void prepare(const State *) {}
+  __device__ void elem(long i, double *, double &) { y[i] = x[i] * dinv[i]; }
+};
+
+// ------------------------------------------------------------------ operators
+struct Op {
+  psp_mat *mat = nullptr;
+  psp_prec *prec = nullptr;
+  psp_callback cb = nullptr;
+  void *cbctx = nullptr;
+  bool present = false;
+  bool native() const { return mat || prec; }
+};
+
+static Op make_op(const psp_operator *o) {
+  Op r;
+  if (!o) return r;
+  r.mat = o->mat; r.prec = o->prec; r.cb = o->cb; r.cbctx = o->ctx;
+  r.present = (r.mat || r.prec || r.cb);
+  return r;
+}
+
+struct Solve {
+  int n = 0;
+  Op A, K;
+  State *S = nullptr;
+  double *hx = nullptr, *hy = nullptr;   // pinned staging for callbacks
+  bool cb_failed = false;
+  // fused identity / Jacobi(steps == 1) preconditioner: z = r .* dinv (dinv == nullptr: z = r)
+  bool fusedK = false;
+  const double *dinv = nullptr;
+};
+
+static int read_done(Solve &s, int *done) {
+  Ctx &c = ctx();
+  PSP_CUDA(cudaMemcpyAsync(c.h_state, c.state, sizeof(State), cudaMemcpyDeviceToHost, c.stream));
+  PSP_CUDA(cudaStreamSynchronize(c.stream));
+  *done = c.h_state->done;
+  return PSP_OK;
+}
+
+// y := Op(x) through a host callback (vectors staged over PCIe)
+static int apply_callback(Solve &s, const Op &op, const double *dx, double *dy, bool check_done = true) {
+  Ctx &c = ctx();
+  if (check_done) {
+    int done = 0;
+    PSP_TRY(read_done(s, &done));
+    if (done) return PSP_OK;
+  }
+  size_t bytes = sizeof(double) * (size_t)s.n;
+  PSP_CUDA(cudaMemcpyAsync(s.hx, dx, bytes, cudaMemcpyDeviceToHost, c.stream));
+  PSP_CUDA(cudaStreamSynchronize(c.stream));
+  if (op.cb(op.cbctx, s.n, s.hx, s.hy) != 0) {
+    s.cb_failed = true;
+    set_error("operator callback failed");
+    return PSP_ERR_CALLBACK;
+  }
+  PSP_CUDA(cudaMemcpyAsync(dy, s.hy, bytes, cudaMemcpyHostToDevice, c.stream));
+  PSP_CUDA(cudaStreamSynchronize(c.stream));
+  return PSP_OK;
+}
+
+// y := A x, optionally fused with dots against y and a scalar epilogue
+static int apply_A(Solve &s, const double *dx, double *dy, const double *w1 = nullptr,
+                   const double *w2 = nullptr, bool w2_is_y = false, int epilogue = EPI_NONE,
+                   int gate = 0) {
+  if (s.A.mat) {
+    SpmvDots d;
+    d.w1 = w1; d.w2 = w2; d.w2_is_y = w2_is_y ? 1 : 0; d.epilogue = epilogue; d.S = s.S;
+    d.gate = gate;
+    return spmv_launch(s.A.mat, dx, dy, d);
+  }
+  PSP_TRY(apply_callback(s, s.A, dx, dy));
+  if (w1 || w2 || w2_is_y || epilogue != EPI_NONE) {
+    FDots2 f{w1, w2_is_y ? dy : w2, dy};
+    PSP_TRY(launch_map(f, s.n, epilogue, gate));
+  }
+  return PSP_OK;
+}
+
+// y := K^-1 x for a preconditioner that is present and not fused
+static int apply_K(Solve &s, const double *dx, double *dy) {
+  if (s.K.prec) return prec_apply_dev(s.K.prec, dx, dy, s.S);
+  return apply_callback(s, s.K, dx, dy);
+}
+
+// ------------------------------------------------------------------ polling driver
+// Enqueue `body(it)` repeatedly, staying up to two polling chunks ahead of the
+// GPU; stops once the device reports done.  `max_rounds` bounds the number of
+// bodies ever enqueued (the device stops by itself through maxit).
+template <class Body>
+static int run_until_done(Solve &s, long long max_rounds, bool sync_each, Body body) {
+  Ctx &c = ctx();
+  long long chunk = c.poll_chunk > 0 ? c.poll_chunk : 8;
+  int slot = 0;
+  bool pending[2] = {false, false};
+  long long rounds = 0;
+  for (;;) {
+    if (pending[slot]) {
+      bool was_idle = (cudaEventQuery(c.evpoll[slot]) == cudaSuccess);
+      PSP_CUDA(cudaEventSynchronize(c.evpoll[slot]));
+      pending[slot] = false;
+      if (c.h_state[slot].done) return PSP_OK;
+      if (was_idle && c.poll_chunk <= 0 && chunk < 128) chunk *= 2;
+    }
+    if (rounds >= max_rounds) break;
+    for (long long j = 0; j < chunk && rounds < max_rounds; j++, rounds++) {
+      PSP_TRY(body(rounds));
+      if (sync_each) {
+        int done = 0;
+        PSP_TRY(read_done(s, &done));
+        if (done) return PSP_OK;
+      }
+    }
+    PSP_CUDA(cudaMemcpyAsync(&c.h_state[slot], c.state, sizeof(State), cudaMemcpyDeviceToHost, c.stream));
+    PSP_CUDA(cudaEventRecord(c.evpoll[slot], c.stream));
+    pending[slot] = true;
+    slot ^= 1;
+  }
+  for (int k = 0; k < 2; k++)
+    if (pending[k]) PSP_CUDA(cudaEventSynchronize(c.evpoll[k]));
+  return PSP_OK;
+}
+
+// ====================================================================== PCG
+struct FPcgResid {          // r = b - r (r holds A x); sums r.r and r.(K^-1 r); zero rhs: x = 0
+  static constexpr int NS = 2; static constexpr bool HASMAX = false, TICKET = false;
+  const double *b; double *r, *x; const double *dinv; int zero_rhs;
+  __device__ void prepare(const State *S) { zero_rhs = (S->phase == 1); }
+  __device__ void elem(long i, double *acc, double &) {
+    if (zero_rhs) { x[i] = 0.0; return; }
+    double t = b[i] - r[i];
+    r[i] = t;
+    acc[0] += t * t;
+    double z = dinv ? t * dinv[i] : t;
+    acc[1] += t * z;
+  }
+};
+struct FPcgP {              // p = z + beta p   (first iteration: p = z), pcg.c:105-115
+  static constexpr int NS = 0; static constexpr bool HASMAX = false, TICKET = false;
+  const double *z, *dinv; double *p; double beta; int first;
+  __device__ void prepare(const State *S) { beta = S->v[V_BETA]; first = (S->it == 1); }
+  __device__ void elem(long i, double *, double &) {
+    double zi = dinv ? z[i] * dinv[i] : z[i];
+    p[i] = first ? zi : zi + beta * p[i];
+  }
+};
+struct FPcgUpdate {         // stagnation scan, x += alpha p, r -= alpha q, |r|^2 (and r.K^-1 r)
+  static constexpr int NS = 2; static constexpr bool HASMAX = true, TICKET = false;
+  const double *p, *q, *dinv; double *x, *r; double alpha; int scan;
+  __device__ void prepare(const State *S) { alpha = S->v[V_ALPHA]; scan = (S->stag == 0); }
+  __device__ void elem(long i, double *acc, double &mx) {
+    double xi = x[i], pi = p[i];
+    if (scan) {             // pcg.c:128-139
+      if (xi != 0.0) mx = fmax(mx, fabs(alpha * pi / xi));
+      else if (pi != 0.0) mx = fmax(mx, 1.0);
+    }
+    x[i] = xi + alpha * pi;
+    double t = r[i] + (-alpha) * q[i];
+    r[i] = t;
+    acc[0] += t * t;
+    double z = dinv ? t * dinv[i] : t;
+    acc[1] += t * z;
+  }
+};
+
+static int solve_pcg(Solve &s, const double *b, double *x, double *work) {
+  const long n = s.n;
+  double *r = work, *z = work + n, *p = work + 2 * n, *q = work + 3 * n;
+  PSP_TRY(launch_map(FNormSq{b}, n, EPI_PCG_NORMB));
+  PSP_TRY(apply_A(s, x, r));
+  PSP_TRY(launch_map(FPcgResid{b, r, x, s.dinv, 0}, n, s.fusedK ? EPI_PCG_RESID0_J : EPI_PCG_RESID0));
+  const bool sync_each = !(s.A.mat && (s.fusedK || s.K.prec));
+  auto body = [&](long long) -> int {
+    if (s.fusedK) {
+      PSP_TRY(launch_map(FPcgP{r, s.dinv, p, 0.0, 0}, n));
+    } else {
+      PSP_TRY(apply_K(s, r, z));
+      PSP_TRY(launch_map(FDot{r, z}, n, EPI_PCG_RHO));
+      PSP_TRY(launch_map(FPcgP{z, nullptr, p, 0.0, 0}, n));
+    }
+    PSP_TRY(apply_A(s, p, q, p, nullptr, false, EPI_PCG_PQ));
+    PSP_TRY(launch_map(FPcgUpdate{p, q, s.fusedK ? s.dinv : nullptr, x, r, 0.0, 0}, n,
+                       s.fusedK ? EPI_PCG_UPDATE_J : EPI_PCG_UPDATE));
+    return PSP_OK;
+  };
+  return run_until_done(s, (long long)ctx().h_state[0].maxit + 1, sync_each, body);
+}
+
+// ====================================================================== MINRES
+struct FMinresInit {        // vh = b - vh (vh holds A x0); |vh|^2; clears vh_old, w, w_old
+  static constexpr int NS = 1; static constexpr bool HASMAX = false, TICKET = false;
+  const double *b; double *vh, *vh_old, *w, *w_old;
+  __device__ void prepare(const State *) {}
+  __device__ void elem(long i, double *acc, double &) {
+    double t = b[i] - vh[i];
+    vh[i] = t; vh_old[i] = 0.0; w[i] = 0.0; w_old[i] = 0.0;
+    acc[0] += t * t;
+  }
+};
+struct FDotK {              // red0 = sum a_i * (K^-1 a)_i with K identity / diagonal; writes y if given
+  static constexpr int NS = 1; static constexpr bool HASMAX = false, TICKET = false;
+  const double *a, *dinv; double *y;
+  __device__ void prepare(const State *) {}
+  __device__ void elem(long i, double *acc, double &) {
+    double t = a[i];
+    double z = dinv ? t * dinv[i] : t;
+    if (y) y[i] = z;
+    acc[0] += t * z;
+  }
+};
+struct FMinresV {           // v = y / beta   (minres.c:124-125)
+  static constexpr int NS = 0; static constexpr bool HASMAX = false, TICKET = false;
+  const double *y; double *v; double beta;
+  __device__ void prepare(const State *S) { beta = S->v[M_BETA]; }
+  __device__ void elem(long i, double *, double &) { v[i] = y[i] / beta; }
+};
+template <bool FUSED>
+struct FMinresLanczos {     // vh_new = av - k1 vh - k2 vh_old; vh_old = vh  (minres.c:131-135)
+  static constexpr int NS = FUSED ? 1 : 0; static constexpr bool HASMAX = false, TICKET = false;
+  const double *av, *dinv; double *vh, *vh_old, *y; double k1, k2;
+  __device__ void prepare(const State *S) { k1 = S->v[M_K1]; k2 = S->v[M_K2]; }
+  __device__ void elem(long i, double *acc, double &) {
+    double old = vh[i];
+    double t = av[i] - k1 * old - k2 * vh_old[i];
+    vh_old[i] = old;
+    vh[i] = t;
+    if (FUSED) {
+      double z = dinv ? t * dinv[i] : t;
+      if (dinv) y[i] = z;
+      acc[0] += t * z;
+    }
+  }
+};
+struct FMinresUpdate {      // w, w_old, x update (minres.c:176-184) + loop test epilogue
+  static constexpr int NS = 0; static constexpr bool HASMAX = false, TICKET = true;
+  const double *v; double *w, *w_old, *x; double r1, r2, r3, step;
+  __device__ void prepare(const State *S) {
+    r1 = S->v[M_R1]; r2 = S->v[M_R2]; r3 = S->v[M_R3]; step = S->v[M_STEP];
+  }
+  __device__ void elem(long i, double *, double &) {
+    double keep = w[i];
+    double wn = (v[i] - r3 * w_old[i] - r2 * keep) / r1;
+    w[i] = wn; w_old[i] = keep;
+    x[i] += step * wn;
+  }
+};
+
+static int solve_minres(Solve &s, const double *b, double *x, double *work) {
+  const long n = s.n;
+  double *vh_old = work, *vh = work + n, *ybuf = work + 2 * n, *w = work + 3 * n,
+         *w_old = work + 4 * n, *v = work + 5 * n, *av = work + 6 * n;
+  // identity preconditioner: y is vh itself (never written separately)
+  double *y = (s.fusedK && !s.dinv) ? vh : ybuf;
+  PSP_TRY(apply_A(s, x, vh));
+  PSP_TRY(launch_map(FMinresInit{b, vh, vh_old, w, w_old}, n, EPI_MINRES_R0));
+  if (s.fusedK) {
+    PSP_TRY(launch_map(FDotK{vh, s.dinv, s.dinv ? y : nullptr}, n, EPI_MINRES_BETA0));
+  } else {
+    PSP_TRY(apply_K(s, vh, y));
+    PSP_TRY(launch_map(FDot{vh, y}, n, EPI_MINRES_BETA0));
+  }
+  const bool sync_each = !(s.A.mat && (s.fusedK || s.K.prec));
+  auto body = [&](long long) -> int {
+    PSP_TRY(launch_map(FMinresV{y, v, 0.0}, n));
+    PSP_TRY(apply_A(s, v, av, v, nullptr, false, EPI_MINRES_ALPHA));
+    if (s.fusedK) {
+      PSP_TRY(launch_map(FMinresLanczos<true>{av, s.dinv, vh, vh_old, y, 0.0, 0.0}, n, EPI_MINRES_BETA));
+    } else {
+      PSP_TRY(launch_map(FMinresLanczos<false>{av, nullptr, vh, vh_old, y, 0.0, 0.0}, n));
+      PSP_TRY(apply_K(s, vh, y));
+      PSP_TRY(launch_map(FDot{vh, y}, n, EPI_MINRES_BETA));
+    }
+    PSP_TRY(launch_map(FMinresUpdate{v, w, w_old, x, 0, 0, 0, 0}, n, EPI_MINRES_LOOP));
+    return PSP_OK;
+  };
+  return run_until_done(s, (long long)ctx().h_state[0].maxit + 1, sync_each, body);
+}
+
+// ====================================================================== QMRS
+struct FQmrsInit0 {         // v = b ; |b|^2            (qmrs.c:68-69)
+  static constexpr int NS = 1; static constexpr bool HASMAX = false, TICKET = false;
+  const double *b; double *v;
+  __device__ void prepare(const State *) {}
+  __device__ void elem(long i, double *acc, double &) { double t = b[i]; v[i] = t; acc[0] += t * t; }
+};
+struct FQmrsInit1 {         // v /= rho0 ; p = g = d = x = 0   (qmrs.c:71-77) + first loop test
+  static constexpr int NS = 0; static constexpr bool HASMAX = false, TICKET = true;
+  double *v, *p, *g, *d, *x; double rho0;
+  __device__ void prepare(const State *S) { rho0 = S->v[Q_RHO0]; }
+  __device__ void elem(long i, double *, double &) {
+    v[i] = v[i] / rho0; p[i] = 0.0; g[i] = 0.0; d[i] = 0.0; x[i] = 0.0;
+  }
+};
+struct FQmrsPG {            // p = v - p cc ; g = t0 - g cc   (qmrs.c:101-105)
+  static constexpr int NS = 0; static constexpr bool HASMAX = false, TICKET = false;
+  const double *v, *t0, *dinv; double *p, *g; double cc;
+  __device__ void prepare(const State *S) { cc = S->v[Q_CC]; }
+  __device__ void elem(long i, double *, double &) {
+    double vi = v[i];
+    double ti = t0 ? t0[i] : (dinv ? vi * dinv[i] : vi);
+    p[i] = vi - p[i] * cc;
+    g[i] = ti - g[i] * cc;
+  }
+};
+struct FQmrsV {             // v = t - v beta ; |v|^2   (qmrs.c:108-111)
+  static constexpr int NS = 1; static constexpr bool HASMAX = false, TICKET = false;
+  const double *t; double *v; double beta;
+  __device__ void prepare(const State *S) { beta = S->v[Q_BETA]; }
+  __device__ void elem(long i, double *acc, double &) {
+    double nv = t[i] - v[i] * beta;
+    v[i] = nv;
+    acc[0] += nv * nv;
+  }
+};
+struct FQmrsUpdate {        // d = p eta + d cc ; x += d ; v *= 1/rho1   (qmrs.c:131-135)
+  static constexpr int NS = 0; static constexpr bool HASMAX = false, TICKET = true;
+  const double *p; double *d, *x, *v; double eta, cc, inv;
+  __device__ void prepare(const State *S) { eta = S->v[Q_ETA]; cc = S->v[Q_CC2]; inv = S->v[Q_INV]; }
+  __device__ void elem(long i, double *, double &) {
+    double di = p[i] * eta + d[i] * cc;
+    d[i] = di;
+    x[i] += di;
+    v[i] *= inv;
+  }
+};
+
+static int solve_qmrs(Solve &s, const double *b, double *x, double *work) {
+  const long n = s.n;
+  double *t0 = work, *p = work + n, *d = work + 2 * n, *v = work + 3 * n, *t = work + 4 * n,
+         *g = work + 5 * n;
+  PSP_TRY(launch_map(FQmrsInit0{b, v}, n, EPI_QMRS_RHO0));
+  PSP_TRY(launch_map(FQmrsInit1{v, p, g, d, x, 0.0}, n, EPI_QMRS_LOOP));
+  const bool sync_each = !(s.A.mat && (s.fusedK || s.K.prec));
+  auto body = [&](long long) -> int {
+    if (s.fusedK) {
+      PSP_TRY(launch_map(FDotK{v, s.dinv, nullptr}, n, EPI_QMRS_DELTA));
+      PSP_TRY(launch_map(FQmrsPG{v, nullptr, s.dinv, p, g, 0.0}, n));
+    } else {
+      PSP_TRY(apply_K(s, v, t0));
+      PSP_TRY(launch_map(FDot{t0, v}, n, EPI_QMRS_DELTA));
+      PSP_TRY(launch_map(FQmrsPG{v, t0, nullptr, p, g, 0.0}, n));
+    }
+    PSP_TRY(apply_A(s, g, t, g, nullptr, false, EPI_QMRS_EPS));
+    PSP_TRY(launch_map(FQmrsV{t, v, 0.0}, n, EPI_QMRS_RHO1));
+    PSP_TRY(launch_map(FQmrsUpdate{p, d, x, v, 0, 0, 0}, n, EPI_QMRS_LOOP));
+    return PSP_OK;
+  };
+  PSP_TRY(run_until_done(s, (long long)ctx().h_state[0].maxit + 1, sync_each, body));
+  // final x <- K^-1 x after a regular loop exit (qmrs.c:146-149)
+  Ctx &c = ctx();
+  State hs;
+  PSP_CUDA(cudaMemcpyAsync(c.h_state, c.state, sizeof(State), cudaMemcpyDeviceToHost, c.stream));
+  PSP_CUDA(cudaStreamSynchronize(c.stream));
+  hs = *c.h_state;
+  if (hs.phase == 2 && s.K.present) {
+    if (s.fusedK) {
+      if (s.dinv) {
+        PSP_TRY(launch_map(FScaleBy{x, s.dinv, t0}, n, EPI_NONE, /*gate=*/3));
+        PSP_CUDA(cudaMemcpyAsync(x, t0, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, c.stream));
+      }
+    } else {
+      if (s.K.prec) PSP_TRY(prec_apply_dev(s.K.prec, x, t0, nullptr));
+      else PSP_TRY(apply_callback(s, s.K, x, t0, /*check_done=*/false));
+      PSP_CUDA(cudaMemcpyAsync(x, t0, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, c.stream));
+    }
+  }
+  return PSP_OK;
+}
+
+// ====================================================================== BiCGSTAB
+struct FBicgInit {          // r = b + -r ; rhat = r ; |r|^2 ; zero rhs: x = 0   (bicgstab.c:207-241)
+  static constexpr int NS = 1; static constexpr bool HASMAX = false, TICKET = false;
+  const double *b; double *r, *rhat, *x; int zero_rhs;
+  __device__ void prepare(const State *S) { zero_rhs = (S->phase == 1); }
+  __device__ void elem(long i, double *acc, double &) {
+    if (zero_rhs) { x[i] = 0.0; return; }
+    double t = b[i] + -r[i];
+    r[i] = t; rhat[i] = t;
+    acc[0] += t * t;
+  }
+};
+struct FBicgP {             // p = r + beta (p - omega v)  (first: p = r); phat = K^-1 p when fused
+  static constexpr int NS = 0; static constexpr bool HASMAX = false, TICKET = false;
+  const double *r, *v, *dinv; double *p, *phat; double beta, omega; int first;
+  __device__ void prepare(const State *S) { beta = S->v[B_BETA]; omega = S->v[B_OMEGA]; first = (S->it == 1); }
+  __device__ void elem(long i, double *, double &) {
+    double pn = first ? r[i] : r[i] + beta * (p[i] - omega * v[i]);
+    p[i] = pn;
+    if (dinv) phat[i] = pn * dinv[i];
+  }
+};
+struct FBicgS {             // s = r + (-alpha) v ; shat = K^-1 s when fused   (bicgstab.c:265)
+  static constexpr int NS = 0; static constexpr bool HASMAX = false, TICKET = false;
+  const double *r, *v, *dinv; double *s, *shat; double alpha;
+  __device__ void prepare(const State *S) { alpha = S->v[B_ALPHA]; }
+  __device__ void elem(long i, double *, double &) {
+    double sn = r[i] + (-alpha) * v[i];
+    s[i] = sn;
+    if (dinv) shat[i] = sn * dinv[i];
+  }
+};
+struct FBicgUpdate {        // x += alpha phat + omega shat ; r = s - omega t ; |r|^2 ; rhat.r
+  static constexpr int NS = 2; static constexpr bool HASMAX = false, TICKET = false;
+  const double *phat, *shat, *s, *t, *rhat; double *x, *r; double alpha, omega;
+  __device__ void prepare(const State *S) { alpha = S->v[B_ALPHA]; omega = S->v[B_OMEGA]; }
+  __device__ void elem(long i, double *acc, double &) {
+    x[i] = x[i] + alpha * phat[i] + omega * shat[i];
+    double rn = s[i] - omega * t[i];
+    r[i] = rn;
+    acc[0] += rn * rn;
+    acc[1] += rhat[i] * rn;
+  }
+};
+
+static int solve_bicgstab(Solve &s, const double *b, double *x, double *work) {
+  const long n = s.n;
+  double *r = work, *rhat = work + n, *p = work + 2 * n, *phatb = work + 3 * n, *v = work + 4 * n,
+         *sv = work + 5 * n, *shatb = work + 6 * n, *t = work + 7 * n;
+  const bool ident = s.fusedK && !s.dinv;
+  double *phat = ident ? p : phatb, *shat = ident ? sv : shatb;
+  PSP_TRY(launch_map(FNormSq{b}, n, EPI_BICG_NORMB));
+  PSP_TRY(apply_A(s, x, r));
+  PSP_TRY(launch_map(FBicgInit{b, r, rhat, x, 0}, n, EPI_BICG_RES0));
+  const bool sync_each = !(s.A.mat && (s.fusedK || s.K.prec));
+  auto body = [&](long long) -> int {
+    PSP_TRY(launch_map(FBicgP{r, v, s.fusedK ? s.dinv : nullptr, p, phat, 0, 0, 0}, n));
+    if (!s.fusedK) PSP_TRY(apply_K(s, p, phat));
+    PSP_TRY(apply_A(s, phat, v, rhat, nullptr, false, EPI_BICG_ALPHA));
+    PSP_TRY(launch_map(FBicgS{r, v, s.fusedK ? s.dinv : nullptr, sv, shat, 0}, n));
+    if (!s.fusedK) PSP_TRY(apply_K(s, sv, shat));
+    PSP_TRY(apply_A(s, shat, t, sv, nullptr, true, EPI_BICG_OMEGA));
+    PSP_TRY(launch_map(FBicgUpdate{phat, shat, sv, t, rhat, x, r, 0, 0}, n, EPI_BICG_RES));
+    return PSP_OK;
+  };
+  return run_until_done(s, (long long)ctx().h_state[0].maxit + 1, sync_each, body);
+}
+
+// ====================================================================== CGS
+struct FCgsInit {           // r0 = b - A x0 ; r = u = p = r0 ; r0.r0 ; b.b   (cgs.c:43-56)
+  static constexpr int NS = 2; static constexpr bool HASMAX = false, TICKET = false;
+  const double *b, *ax; double *r0, *r, *u, *p;
+  __device__ void prepare(const State *) {}
+  __device__ void elem(long i, double *acc, double &) {
+    double bi = b[i];
+    double t = bi + (-1.0) * ax[i];
+    r0[i] = t; r[i] = t; u[i] = t; p[i] = t;
+    acc[0] += t * t;
+    acc[1] += bi * bi;
+  }
+};
+struct FCgsQ {              // q = u - alpha v ; ta = u + q ; tb = K^-1 ta when fused   (cgs.c:74-79)
+  static constexpr int NS = 0; static constexpr bool HASMAX = false, TICKET = false;
+  const double *u, *v, *dinv; double *q, *ta, *tb; double alpha;
+  __device__ void prepare(const State *S) { alpha = S->v[C_ALPHA]; }
+  __device__ void elem(long i, double *, double &) {
+    double ui = u[i];
+    double qi = ui + (-alpha) * v[i];
+    q[i] = qi;
+    double ti = ui + 1.0 * qi;
+    ta[i] = ti;
+    if (dinv) tb[i] = ti * dinv[i];
+  }
+};
+struct FCgsUpdate {         // x += alpha tb ; r -= alpha tc ; r.r ; r.r0   (cgs.c:84-95)
+  static constexpr int NS = 2; static constexpr bool HASMAX = false, TICKET = false;
+  const double *tb, *tc, *r0; double *x, *r; double alpha;
+  __device__ void prepare(const State *S) { alpha = S->v[C_ALPHA]; }
+  __device__ void elem(long i, double *acc, double &) {
+    x[i] = x[i] + alpha * tb[i];
+    double rn = r[i] + (-alpha) * tc[i];
+    r[i] = rn;
+    acc[0] += rn * rn;
+    acc[1] += rn * r0[i];
+  }
+};
+struct FCgsUP {             // u = r + beta q ; p = u + beta (q + beta p)   (cgs.c:100-105)
+  static constexpr int NS = 0; static constexpr bool HASMAX = false, TICKET = true;
+  const double *r, *q; double *u, *p; double beta;
+  __device__ void prepare(const State *S) { beta = S->v[C_BETA]; }
+  __device__ void elem(long i, double *, double &) {
+    double qi = q[i];
+    double un = r[i] + beta * qi;
+    u[i] = un;
+    double tt = qi + beta * p[i];
+    p[i] = un + beta * tt;
+  }
+};
+
+static int solve_cgs(Solve &s, const double *b, double *x, double *work) {
+  const long n = s.n;
+  double *r0 = work, *r = work + n, *p = work + 2 * n, *q = work + 3 * n, *u = work + 4 * n,
+         *v = work + 5 * n, *ta = work + 6 * n, *tbb = work + 7 * n, *tc = work + 8 * n;
+  const bool ident = s.fusedK && !s.dinv;
+  PSP_TRY(apply_A(s, x, ta));
+  PSP_TRY(launch_map(FCgsInit{b, ta, r0, r, u, p}, n, EPI_CGS_INIT));
+  const bool sync_each = !(s.A.mat && (s.fusedK || s.K.prec));
+  auto body = [&](long long) -> int {
+    const double *kp = p;                       // K^-1 p
+    if (s.fusedK) {
+      if (s.dinv) { PSP_TRY(launch_map(FScaleBy{p, s.dinv, ta}, n)); kp = ta; }
+    } else {
+      PSP_TRY(apply_K(s, p, ta)); kp = ta;
+    }
+    PSP_TRY(apply_A(s, kp, v, r0, nullptr, false, EPI_CGS_ALPHA));
+    double *tb = ident ? ta : tbb;
+    PSP_TRY(launch_map(FCgsQ{u, v, s.fusedK ? s.dinv : nullptr, q, ta, tb, 0}, n));
+    if (!s.fusedK) PSP_TRY(apply_K(s, ta, tb));
+    PSP_TRY(apply_A(s, tb, tc));
+    PSP_TRY(launch_map(FCgsUpdate{tb, tc, r0, x, r, 0}, n, EPI_CGS_RES));
+    PSP_TRY(launch_map(FCgsUP{r, q, u, p, 0}, n, EPI_CGS_LOOP));
+    return PSP_OK;
+  };
+  return run_until_done(s, (long long)ctx().h_state[0].maxit + 1, sync_each, body);
+}
+
+// ====================================================================== GMRES
+struct FGmresResid {        // V0 = V0 - b (V0 holds A x) ; |V0|^2 ; zero rhs: x = 0   (gmres.c:102-116)
+  static constexpr int NS = 1; static constexpr bool HASMAX = false, TICKET = false;
+  const double *b; double *v0, *x; int zero_rhs;
+  __device__ void prepare(const State *S) { zero_rhs = (S->phase == 1); }
+  __device__ void elem(long i, double *acc, double &) {
+    if (zero_rhs) { x[i] = 0.0; return; }
+    double t = v0[i] + (-1.0) * b[i];
+    v0[i] = t;
+    acc[0] += t * t;
+  }
+};
+struct FGmresScale {        // a *= scalar slot (dscal)   (gmres.c:117,:150)
+  static constexpr int NS = 0; static constexpr bool HASMAX = false, TICKET = false;
+  double *a; int slot; double f;
+  __device__ void prepare(const State *S) { f = S->v[slot]; }
+  __device__ void elem(long i, double *, double &) { a[i] = f * a[i]; }
+};
+struct FGmresMgs {          // vn -= H(k,i) vk ; red0 = <vn, vnext>   (gmres.c:141-148)
+  static constexpr int NS = 1; static constexpr bool HASMAX = false, TICKET = false;
+  const double *vk, *vnext; double *vn; double h;
+  __device__ void prepare(const State *S) { h = S->v[G_HK]; }
+  __device__ void elem(long i, double *acc, double &) {
+    double t = vn[i] + (-h) * vk[i];
+    vn[i] = t;
+    acc[0] += t * (vnext ? vnext[i] : t);
+  }
+};
+struct FGmresX {            // x += sum_{j<=last} g[j] W(j)   (gmres.c:177-181) + outer loop test
+  static constexpr int NS = 0; static constexpr bool HASMAX = false, TICKET = true;
+  const double *W; double *x; const double *g; long n; int last;
+  __device__ void prepare(const State *S) { last = S->last_i; }
+  __device__ void elem(long i, double *, double &) {
+    double xi = x[i];
+    for (int j = 0; j <= last; j++) xi = xi + g[j] * W[(size_t)j * n + i];
+    x[i] = xi;
+  }
+};
+
+static int solve_gmres(Solve &s, const double *b, double *x, int m) {
+  Ctx &c = ctx();
+  const long n = s.n;
+  const size_t N = (size_t)n;
+  double *V = nullptr, *W = nullptr, *small = nullptr;
+  const bool ident = s.fusedK && !s.dinv;
+  auto cleanup = [&]() { cudaFree(V); if (!ident) cudaFree(W); cudaFree(small); };
+  if (cudaMalloc((void **)&V, sizeof(double) * N * (size_t)(m + 1)) != cudaSuccess ||
+      (!ident && cudaMalloc((void **)&W, sizeof(double) * N * (size_t)m) != cudaSuccess) ||
+      cudaMalloc((void **)&small, sizeof(double) * ((size_t)(m + 1) * m + (m + 1) + 2 * (size_t)m)) != cudaSuccess) {
+    cudaGetLastError();
+    cleanup();
+    set_error("gmres: out of device memory for the Krylov basis (n=%ld, m=%d)", n, m);
+    return PSP_ERR_NOMEM;
+  }
+  if (ident) W = V;
+  GmresSmall G;
+  G.H = small; G.g = small + (size_t)(m + 1) * m; G.cs = G.g + (m + 1); G.sn = G.cs + m;
+  cudaMemcpyAsync((void *)(c.state + 1), &G, sizeof G, cudaMemcpyHostToDevice, c.stream);
+  int st = PSP_OK;
+  auto run = [&]() -> int {
+    PSP_TRY(launch_map(FNormSq{b}, n, EPI_GMRES_NORMB));
+    const bool sync_each = false;
+    auto cycle = [&](long long) -> int {
+      PSP_TRY(apply_A(s, x, V));
+      PSP_TRY(launch_map(FGmresResid{b, V, x, 0}, n, EPI_GMRES_BETA));
+      PSP_TRY(launch_map(FGmresScale{V, G_SCALE0, 0}, n));
+      for (int i = 0; i < m; i++) {
+        double *vi = V + (size_t)i * N, *vn = V + (size_t)(i + 1) * N, *wi = W + (size_t)i * N;
+        if (s.fusedK) {
+          if (s.dinv) PSP_TRY(launch_map(FScaleBy{vi, s.dinv, wi}, n, EPI_NONE, 1));
+        } else {
+          if (s.K.prec) PSP_TRY(prec_apply_dev(s.K.prec, vi, wi, s.S));
+          else {
+            // callback: must not run once the cycle is over
+            PSP_CUDA(cudaMemcpyAsync(c.h_state, c.state, sizeof(State), cudaMemcpyDeviceToHost, c.stream));
+            PSP_CUDA(cudaStreamSynchronize(c.stream));
+            if (c.h_state->done || c.h_state->cyc_done) break;
+            PSP_TRY(apply_callback(s, s.K, vi, wi, false));
+          }
+        }
+        if (!s.A.mat) {
+          PSP_CUDA(cudaMemcpyAsync(c.h_state, c.state, sizeof(State), cudaMemcpyDeviceToHost, c.stream));
+          PSP_CUDA(cudaStreamSynchronize(c.stream));
+          if (c.h_state->done || c.h_state->cyc_done) break;
+        }
+        PSP_TRY(apply_A(s, wi, vn, V, nullptr, false, EPI_GMRES_H, 1));
+        for (int k = 0; k <= i; k++) {
+          const double *vk = V + (size_t)k * N;
+          const double *vnext = (k < i) ? V + (size_t)(k + 1) * N : nullptr;
+          PSP_TRY(launch_map(FGmresMgs{vk, vnext, vn, 0}, n, k < i ? EPI_GMRES_H : EPI_GMRES_HLAST, 1));
+        }
+        PSP_TRY(launch_map(FGmresScale{vn, G_INVH, 0}, n, EPI_NONE, 1));
+      }
+      PSP_TRY(launch_map(FGmresX{W, x, G.g, n, 0}, n, EPI_GMRES_CYCLE));
+      // poll once per restart cycle
+      int done = 0;
+      PSP_TRY(read_done(s, &done));
+      return PSP_OK;
+    };
+    // every cycle performs >= 1 iteration; +2 covers the final true-residual pass
+    long long max_cycles = (long long)c.h_state[0].maxit + 2;
+    for (long long cyc = 0; cyc < max_cycles; cyc++) {
+      PSP_TRY(cycle(cyc));
+      if (c.h_state->done) break;
+    }
+    (void)sync_each;
+    return PSP_OK;
+  };
+  st = run();
+  cudaStreamSynchronize(c.stream);
+  cleanup();
+  return st;
+}
+
+// ====================================================================== entry
+static size_t work_vectors(int solver) {
+  switch (solver) {
+  case PSP_PCG: return 4;        // itsolversmodule.c:90
+  case PSP_MINRES: return 7;     // :278
+  case PSP_QMRS: return 6;       // :467
+  case PSP_BICGSTAB: return 8;   // :182
+  case PSP_CGS: return 9;        // :560 (8) + one extra so the SpMV is never in place
+  default: return 0;             // gmres allocates V, W itself (gmres.c:84-96)
+  }
+}
+
+int solve_dev(int solver, const psp_operator *Aop, const psp_operator *Kop, int n, const double *db,
+              double *dx, double tol, int maxit, int gmres_dim, int *info, int *iter, double *relres) {
+  PSP_TRY(ensure_init());
+  Ctx &c = ctx();
+  if (solver < 0 || solver > PSP_GMRES) { set_error("unknown solver id %d", solver); return PSP_ERR_ARG; }
+  if (n < 0 || !Aop) { set_error("psp_solve: bad arguments"); return PSP_ERR_ARG; }
+  Solve s;
+  s.n = n;
+  s.A = make_op(Aop);
+  s.K = make_op(Kop);
+  s.S = c.state;
+  if (!s.A.present) { set_error("psp_solve: operator A is empty"); return PSP_ERR_ARG; }
+  if (s.A.mat && (s.A.mat->m != n || s.A.mat->n != n)) { set_error("psp_solve: matrix is not n x n"); return PSP_ERR_ARG; }
+  if (s.K.prec && s.K.prec->n != n) { set_error("psp_solve: preconditioner order mismatch"); return PSP_ERR_ARG; }
+  if (solver == PSP_GMRES && gmres_dim < 1) { set_error("gmres: dim must be >= 1"); return PSP_ERR_ARG; }
+  // identity and single-step Jacobi preconditioners are fused into the vector kernels
+  if (!s.K.present) { s.fusedK = true; s.dinv = nullptr; }
+  else if (s.K.prec && s.K.prec->kind == 1 && s.K.prec->steps == 1) { s.fusedK = true; s.dinv = s.K.prec->d_dinv; }
+
+  double *work = nullptr;
+  size_t nw = work_vectors(solver);
+  if (nw) {
+    if (cudaMalloc((void **)&work, sizeof(double) * nw * (size_t)(n > 0 ? n : 1)) != cudaSuccess) {
+      cudaGetLastError();
+      set_error("psp_solve: out of device memory for %zu work vectors of length %d", nw, n);
+      return PSP_ERR_NOMEM;
+    }
+  }
+  if (s.A.cb || s.K.cb) {
+    if (cudaHostAlloc((void **)&s.hx, sizeof(double) * (size_t)(n > 0 ? n : 1), cudaHostAllocDefault) != cudaSuccess ||
+        cudaHostAlloc((void **)&s.hy, sizeof(double) * (size_t)(n > 0 ? n : 1), cudaHostAllocDefault) != cudaSuccess) {
+      cudaGetLastError();
+      cudaFree(work); cudaFreeHost(s.hx); cudaFreeHost(s.hy);
+      set_error("psp_solve: out of pinned host memory");
+      return PSP_ERR_NOMEM;
+    }
+  }
+  State init;
+  memset(&init, 0, sizeof init);
+  init.maxit = maxit; init.tol = tol; init.mdim = gmres_dim;
+  init.iter = -1; init.relres = nan("");
+  c.h_state[0] = init;
+  c.h_state[1] = init;
+  int st = PSP_OK;
+  auto go = [&]() -> int {
+    PSP_CUDA(cudaMemcpyAsync(c.state, &c.h_state[0], sizeof(State), cudaMemcpyHostToDevice, c.stream));
+    PSP_CUDA(cudaStreamSynchronize(c.stream));
+    c.h_state[0].done = 0; c.h_state[1].done = 0;
+    PSP_CUDA(cudaEventRecord(c.ev0, c.stream));
+    switch (solver) {
+    case PSP_PCG: PSP_TRY(solve_pcg(s, db, dx, work)); break;
+    case PSP_MINRES: PSP_TRY(solve_minres(s, db, dx, work)); break;
+    case PSP_QMRS: PSP_TRY(solve_qmrs(s, db, dx, work)); break;
+    case PSP_BICGSTAB: PSP_TRY(solve_bicgstab(s, db, dx, work)); break;
+    case PSP_CGS: PSP_TRY(solve_cgs(s, db, dx, work)); break;
+    case PSP_GMRES: PSP_TRY(solve_gmres(s, db, dx, gmres_dim)); break;
+    }
+    PSP_CUDA(cudaEventRecord(c.ev1, c.stream));
+    PSP_CUDA(cudaMemcpyAsync(&c.h_state[0], c.state, sizeof(State), cudaMemcpyDeviceToHost, c.stream));
+    PSP_CUDA(cudaStreamSynchronize(c.stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c.ev0, c.ev1);
+    c.last_ms = ms;
+    return PSP_OK;
+  };
+  st = go();
+  if (st != PSP_OK) cudaStreamSynchronize(c.stream);
+  cudaFree(work);
+  if (s.hx) cudaFreeHost(s.hx);
+  if (s.hy) cudaFreeHost(s.hy);
+  if (st != PSP_OK) return st;
+  const State &R = c.h_state[0];
+  if (info) *info = R.info;
+  if (iter) *iter = R.iter;
+  if (relres) *relres = R.relres;
+  return PSP_OK;
+}
+
+}  // namespace psp
+
+using namespace psp;
+
+extern "C" int psp_solve_dev(int solver, const psp_operator *A, const psp_operator *K, int n,
+                             const double *db, double *dx, double tol, int maxit, int gmres_dim,
+                             int *info, int *iter, double *relres) {
+  return solve_dev(solver, A, K, n, db, dx, tol, maxit, gmres_dim, info, iter, relres);
+}
+
+extern "C" int psp_solve(int solver, const psp_operator *A, const psp_operator *K, int n,
+                         const double *b, double *x, double tol, int maxit, int gmres_dim,
+                         int *info, int *iter, double *relres) {
+  if (n < 0 || (n > 0 && (!b || !x))) { set_error("psp_solve: NULL vector"); return PSP_ERR_ARG; }
+  PSP_TRY(ensure_init());
+  double *db = nullptr, *dx = nullptr;
+  PSP_TRY(psp_vec_alloc((size_t)n, &db));
+  int st = psp_vec_alloc((size_t)n, &dx);
+  if (st == PSP_OK) st = psp_vec_upload(db, b, (size_t)n, 1);
+  if (st == PSP_OK) st = psp_vec_upload(dx, x, (size_t)n, 1);
+  if (st == PSP_OK) st = solve_dev(solver, A, K, n, db, dx, tol, maxit, gmres_dim, info, iter, relres);
+  if (st == PSP_OK) st = psp_vec_download(dx, x, (size_t)n, 1);
+  psp_vec_free(db);
+  psp_vec_free(dx);
+  return st;
+}

@@ -1,0 +1,424 @@
+// psp_spmv.cu -- fp64 CSR / SSS sparse matrix-vector product for sm_100a.
+//
+// Replaces csr_matvec_kernel / csr_matvec_transp_kernel (pysparse/sparse/src/
+// csr_mat.c:17-106) and sss_matvec (sss_mat.c:40-76).
+//
+// Kernel design ("row-block streaming"):
+//   * an analysis pass on the host bins consecutive rows into row blocks of
+//     at most kBlkNnz stored entries and kThreads rows; a row longer than
+//     kBlkNnz gets a block of its own;
+//   * a persistent grid (a multiple of the SM count) walks the row blocks.
+//     For a block, ALL threads stream the block's contiguous val/col range
+//     with aligned 128-bit loads (fully coalesced, independent of the row
+//     lengths), gather x through the read-only path, and park the products
+//     in shared memory; then one thread per row adds its products up IN ROW
+//     ORDER.  The row sums therefore have exactly the accumulation order of
+//     the reference's serial loop, and since the products are rounded before
+//     they are added (no FMA) short-row results are bit-identical to it;
+//   * blocks whose rows are long on average are reduced warp-per-row, and a
+//     single over-long row is reduced by the whole CTA (tree order; within
+//     the 1e-13 contract);
+//   * optional fused epilogue: up to two dot products with the result vector
+//     (p.q for PCG, rhat.v / t.s / t.t for BiCGSTAB ...), reduced
+//     deterministically, followed by the solver's scalar epilogue.
+//
+// Transposed product: a one-time transpose index (CSR of A^T, built on the
+// host with a counting sort that keeps ascending row order) turns the
+// reference's scatter loop into the same gather kernel -- deterministic, no
+// fp64 atomics, and again the reference's accumulation order.
+//
+// SSS: the strict lower triangle is expanded once into the symmetric CSR in
+// ll_mat.to_csr() order (lower row | diag | upper = transposed lower, rows
+// ascending), which is exactly the order in which sss_matvec accumulates
+// y[i]; the lower triangle + diagonal are kept as well for the SSOR sweeps.
+#include "psp_mat.cuh"
+#include "psp_epilogue.cuh"
+
+namespace psp {
+
+constexpr int kBlkNnz = 2044;             // products per row block (+4 slack for alignment)
+constexpr int kProdSlots = kBlkNnz + 4;
+
+struct SpmvArgs {
+  const int *ind, *col, *blk;
+  const double *val, *x;
+  double *y;
+  int nb;
+  const double *w1, *w2;
+  int w2_is_y;
+  int epilogue;
+  int gate;
+  State *S;
+  double *partials;
+  unsigned *ticket;
+  void *aux;
+};
+
+__device__ __forceinline__ double ldg_f64(const double *p) { return __ldg(p); }
+
+// VEC = 0: scalar 8/4-byte loads;  VEC = 1: aligned 128-bit loads (4 entries / thread / step)
+template <int VEC, bool DOTS>
+__global__ void __launch_bounds__(kThreads, 4) k_spmv_stream(SpmvArgs a) {
+  __shared__ __align__(16) double prod[kProdSlots];
+  __shared__ double red_sh[8];
+  if (DOTS) {
+    const volatile State *V = a.S;
+    if (V->done || (a.gate == 1 && V->cyc_done)) return;
+  }
+  const int tid = threadIdx.x;
+  double acc0 = 0.0, acc1 = 0.0;
+
+  for (int b = blockIdx.x; b < a.nb; b += gridDim.x) {
+    const int r0 = __ldg(a.blk + b), r1 = __ldg(a.blk + b + 1);
+    const int k0 = __ldg(a.ind + r0), k1 = __ldg(a.ind + r1);
+    const int nrows = r1 - r0, cnt = k1 - k0;
+
+    if (cnt <= kBlkNnz) {
+      int base;   // prod[j] holds the product of entry base + j
+      if (VEC) {
+        base = k0 & ~3;
+        const int ngroups = (k1 - base + 3) >> 2;
+        for (int g = tid; g < ngroups; g += kThreads) {
+          const int k = base + 4 * g;
+          const int4 c = __ldg(reinterpret_cast<const int4 *>(a.col + k));
+          const double2 v01 = __ldg(reinterpret_cast<const double2 *>(a.val + k));
+          const double2 v23 = __ldg(reinterpret_cast<const double2 *>(a.val + k + 2));
+          double2 p01, p23;
+          p01.x = __dmul_rn(v01.x, ldg_f64(a.x + c.x));
+          p01.y = __dmul_rn(v01.y, ldg_f64(a.x + c.y));
+          p23.x = __dmul_rn(v23.x, ldg_f64(a.x + c.z));
+          p23.y = __dmul_rn(v23.y, ldg_f64(a.x + c.w));
+          *reinterpret_cast<double2 *>(prod + 4 * g) = p01;
+          *reinterpret_cast<double2 *>(prod + 4 * g + 2) = p23;
+        }
+      } else {
+        base = k0;
+#pragma unroll 4
+        for (int k = tid; k < cnt; k += kThreads)
+          prod[k] = __dmul_rn(__ldg(a.val + k0 + k), ldg_f64(a.x + __ldg(a.col + k0 + k)));
+      }
+      __syncthreads();
+      if (cnt <= 16 * nrows) {
+        // short rows: one thread per row, sequential (reference) order
+        if (tid < nrows) {
+          const int r = r0 + tid;
+          const int s = __ldg(a.ind + r) - base, e = __ldg(a.ind + r + 1) - base;
+          double sum = 0.0;
+          for (int k = s; k < e; k++) sum = __dadd_rn(sum, prod[k]);
+          a.y[r] = sum;
+          if (DOTS) {
+            if (a.w1) acc0 += a.w1[r] * sum;
+            if (a.w2_is_y) acc1 += sum * sum;
+            else if (a.w2) acc1 += a.w2[r] * sum;
+          }
+        }
+      } else {
+        // long rows: one warp per row
+        const int w = tid >> 5, l = tid & 31;
+        for (int rr = w; rr < nrows; rr += kThreads / 32) {
+          const int r = r0 + rr;
+          const int s = __ldg(a.ind + r) - base, e = __ldg(a.ind + r + 1) - base;
+          double sum = 0.0;
+          for (int k = s + l; k < e; k += 32) sum += prod[k];
+          sum = warp_sum(sum);
+          if (l == 0) {
+            a.y[r] = sum;
+            if (DOTS) {
+              if (a.w1) acc0 += a.w1[r] * sum;
+              if (a.w2_is_y) acc1 += sum * sum;
+              else if (a.w2) acc1 += a.w2[r] * sum;
+            }
+          }
+        }
+      }
+      __syncthreads();
+    } else {
+      // one over-long row: whole CTA, strided, tree reduction
+      double sum = 0.0;
+      for (int k = k0 + tid; k < k1; k += kThreads)
+        sum += __ldg(a.val + k) * ldg_f64(a.x + __ldg(a.col + k));
+      sum = block_sum(sum, red_sh);
+      if (tid == 0) {
+        a.y[r0] = sum;
+        if (DOTS) {
+          if (a.w1) acc0 += a.w1[r0] * sum;
+          if (a.w2_is_y) acc1 += sum * sum;
+          else if (a.w2) acc1 += a.w2[r0] * sum;
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  if (DOTS) {
+    double mine[2];
+    mine[0] = block_sum(acc0, red_sh);
+    mine[1] = block_sum(acc1, red_sh);
+    double tot[2], dummy;
+    if (grid_reduce_finish<2, false>(mine, 0.0, a.partials, a.ticket, tot, &dummy, red_sh)) {
+      if (tid == 0) {
+        a.S->red[0] = tot[0];
+        a.S->red[1] = tot[1];
+        run_epilogue(a.epilogue, a.S, a.aux);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- host side
+
+static int upload(const void *src, size_t bytes, void **dst, size_t pad_bytes = 64) {
+  void *p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes + pad_bytes);
+  if (e != cudaSuccess) {
+    set_error("cudaMalloc(%zu bytes) failed: %s", bytes + pad_bytes, cudaGetErrorString(e));
+    return PSP_ERR_NOMEM;
+  }
+  PSP_CUDA(cudaMemsetAsync((char *)p + bytes, 0, pad_bytes, ctx().stream));
+  if (bytes) PSP_CUDA(cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, ctx().stream));
+  *dst = p;
+  return PSP_OK;
+}
+
+// Greedy row-block schedule: consecutive rows while the block stays within
+// kBlkNnz entries and kThreads rows; an over-long row is a block by itself.
+static void build_row_blocks(int m, const int *ind, std::vector<int> &blk) {
+  blk.clear();
+  blk.push_back(0);
+  int r = 0;
+  while (r < m) {
+    int start = r;
+    long long base = ind[r];
+    int e = r;
+    while (e < m && (e - start) < kThreads && (long long)ind[e + 1] - base <= kBlkNnz) e++;
+    if (e == start) e = start + 1;   // single row longer than a block
+    blk.push_back(e);
+    r = e;
+  }
+}
+
+static int check_csr(int m, int n, long long nnz, const int *ind, const int *col, bool strict_lower) {
+  if (m < 0 || n < 0 || nnz < 0) { set_error("negative matrix dimension"); return PSP_ERR_ARG; }
+  if (ind[0] != 0 || ind[m] != nnz) { set_error("ind[0] != 0 or ind[m] != nnz"); return PSP_ERR_STRUCTURE; }
+  for (int i = 0; i < m; i++) {
+    if (ind[i + 1] < ind[i]) { set_error("row pointer array not monotone at row %d", i); return PSP_ERR_STRUCTURE; }
+    for (int k = ind[i]; k < ind[i + 1]; k++) {
+      int c = col[k];
+      if (c < 0 || c >= n || (strict_lower && c >= i)) {
+        set_error("column index %d out of range in row %d", c, i);
+        return PSP_ERR_STRUCTURE;
+      }
+    }
+  }
+  return PSP_OK;
+}
+
+static int finish_csr_upload(psp_mat *A, const std::vector<int> &ind, const int *col, const double *val) {
+  std::vector<int> blk;
+  build_row_blocks(A->m, ind.data(), blk);
+  A->nb = (int)blk.size() - 1;
+  PSP_TRY(upload(ind.data(), sizeof(int) * (size_t)(A->m + 1), (void **)&A->d_ind));
+  PSP_TRY(upload(col, sizeof(int) * (size_t)A->fnnz, (void **)&A->d_col));
+  PSP_TRY(upload(val, sizeof(double) * (size_t)A->fnnz, (void **)&A->d_val));
+  PSP_TRY(upload(blk.data(), sizeof(int) * blk.size(), (void **)&A->d_blk));
+  PSP_CUDA(cudaStreamSynchronize(ctx().stream));   // host staging vectors die with this frame
+  return PSP_OK;
+}
+
+int csr_create(int m, int n, long long nnz, const int *ind, const int *col, const double *val,
+               psp_mat **out, bool keep_host) {
+  PSP_TRY(check_csr(m, n, nnz, ind, col, false));
+  psp_mat *A = new psp_mat();
+  A->kind = 1; A->m = m; A->n = n; A->nnz = nnz; A->fnnz = nnz;
+  std::vector<int> hind(ind, ind + m + 1);
+  int st = finish_csr_upload(A, hind, col, val);
+  if (st != PSP_OK) { psp_mat_destroy(A); return st; }
+  if (keep_host) {
+    A->h_ind.swap(hind);
+    A->h_col.assign(col, col + nnz);
+    A->h_val.assign(val, val + nnz);
+  }
+  *out = A;
+  return PSP_OK;
+}
+
+int sss_create(int n, long long nnz, const int *ind, const int *col, const double *val,
+               const double *diag, psp_mat **out) {
+  PSP_TRY(check_csr(n, n, nnz, ind, col, true));
+  long long fnnz = 2 * nnz + n;
+  if (fnnz >= (1LL << 31)) { set_error("expanded SSS matrix exceeds 2^31 entries"); return PSP_ERR_ARG; }
+  psp_mat *A = new psp_mat();
+  A->kind = 2; A->m = n; A->n = n; A->nnz = nnz; A->fnnz = fnnz;
+  // symmetric expansion in to_csr() order (ll_mat.c:1601-1623)
+  std::vector<int> find((size_t)n + 1, 0), fcol((size_t)fnnz), fill((size_t)n);
+  std::vector<double> fval((size_t)fnnz);
+  for (int i = 0; i < n; i++) find[i + 1] = ind[i + 1] - ind[i] + 1;
+  for (long long k = 0; k < nnz; k++) find[col[k] + 1]++;
+  for (int i = 0; i < n; i++) find[i + 1] += find[i];
+  for (int i = 0; i < n; i++) {
+    int p = find[i];
+    for (int k = ind[i]; k < ind[i + 1]; k++) { fcol[p] = col[k]; fval[p] = val[k]; p++; }
+    fcol[p] = i; fval[p] = diag[i]; p++;
+    fill[i] = p;
+  }
+  for (int i = 0; i < n; i++)               // rows ascending => upper parts ascending
+    for (int k = ind[i]; k < ind[i + 1]; k++) {
+      int j = col[k];
+      fcol[fill[j]] = i; fval[fill[j]] = val[k]; fill[j]++;
+    }
+  int st = finish_csr_upload(A, find, fcol.data(), fval.data());
+  if (st == PSP_OK) st = upload(ind, sizeof(int) * (size_t)(n + 1), (void **)&A->d_lind);
+  if (st == PSP_OK) st = upload(col, sizeof(int) * (size_t)nnz, (void **)&A->d_lcol);
+  if (st == PSP_OK) st = upload(val, sizeof(double) * (size_t)nnz, (void **)&A->d_lval);
+  if (st == PSP_OK) st = upload(diag, sizeof(double) * (size_t)n, (void **)&A->d_diag);
+  if (st == PSP_OK && cudaStreamSynchronize(ctx().stream) != cudaSuccess) st = PSP_ERR_CUDA;
+  if (st != PSP_OK) { psp_mat_destroy(A); return st; }
+  A->h_ind.assign(ind, ind + n + 1);
+  A->h_col.assign(col, col + nnz);
+  A->h_val.assign(val, val + nnz);
+  A->h_diag.assign(diag, diag + n);
+  *out = A;
+  return PSP_OK;
+}
+
+// One-time transpose index: CSR of A^T via counting sort over the columns;
+// rows are visited in ascending order, so every row of A^T lists its entries
+// by ascending original row -- the order csr_matvec_transp_kernel
+// (csr_mat.c:74-88) accumulates y[col] in.
+int mat_transpose(psp_mat *A) {
+  if (A->transp) return PSP_OK;
+  if (A->kind != 1) { set_error("transpose index is only built for CSR matrices"); return PSP_ERR_ARG; }
+  const int m = A->m, n = A->n;
+  const long long nnz = A->nnz;
+  std::vector<int> ind, col;
+  std::vector<double> val;
+  if (!A->h_ind.empty()) { ind = A->h_ind; col = A->h_col; val = A->h_val; }
+  else {
+    ind.resize((size_t)m + 1); col.resize((size_t)nnz); val.resize((size_t)nnz);
+    PSP_CUDA(cudaMemcpy(ind.data(), A->d_ind, sizeof(int) * (size_t)(m + 1), cudaMemcpyDeviceToHost));
+    PSP_CUDA(cudaMemcpy(col.data(), A->d_col, sizeof(int) * (size_t)nnz, cudaMemcpyDeviceToHost));
+    PSP_CUDA(cudaMemcpy(val.data(), A->d_val, sizeof(double) * (size_t)nnz, cudaMemcpyDeviceToHost));
+  }
+  std::vector<int> tind((size_t)n + 1, 0), tcol((size_t)nnz), fill((size_t)n);
+  std::vector<double> tval((size_t)nnz);
+  for (long long k = 0; k < nnz; k++) tind[col[k] + 1]++;
+  for (int j = 0; j < n; j++) tind[j + 1] += tind[j];
+  for (int j = 0; j < n; j++) fill[j] = tind[j];
+  for (int i = 0; i < m; i++)
+    for (int k = ind[i]; k < ind[i + 1]; k++) {
+      int j = col[k];
+      tcol[fill[j]] = i; tval[fill[j]] = val[k]; fill[j]++;
+    }
+  psp_mat *T = nullptr;
+  PSP_TRY(csr_create(n, m, nnz, tind.data(), tcol.data(), tval.data(), &T, false));
+  A->transp = T;
+  return PSP_OK;
+}
+
+int spmv_launch(const psp_mat *A, const double *dx, double *dy, const SpmvDots &d) {
+  Ctx &c = ctx();
+  if (A->m == 0) return PSP_OK;
+  SpmvArgs a;
+  a.ind = A->d_ind; a.col = A->d_col; a.blk = A->d_blk; a.val = A->d_val;
+  a.x = dx; a.y = dy; a.nb = A->nb;
+  a.w1 = d.w1; a.w2 = d.w2; a.w2_is_y = d.w2_is_y; a.epilogue = d.epilogue; a.S = d.S;
+  a.gate = d.gate;
+  a.partials = c.partials; a.ticket = c.tickets; a.aux = nullptr;
+  int grid = A->nb;
+  int cap = c.sms * 6;
+  if (cap > kMaxGrid) cap = kMaxGrid;
+  if (grid > cap) grid = cap;
+  const bool vec = (c.spmv_variant != 1);
+  if (d.S) {
+    a.aux = (void *)(d.S + 1);   // solver-specific small state sits right behind the State
+    if (vec) k_spmv_stream<1, true><<<grid, kThreads, 0, c.stream>>>(a);
+    else k_spmv_stream<0, true><<<grid, kThreads, 0, c.stream>>>(a);
+  } else {
+    if (vec) k_spmv_stream<1, false><<<grid, kThreads, 0, c.stream>>>(a);
+    else k_spmv_stream<0, false><<<grid, kThreads, 0, c.stream>>>(a);
+  }
+  PSP_LAUNCH_CHECK();
+  return PSP_OK;
+}
+
+}  // namespace psp
+
+// ---------------------------------------------------------------- C-ABI
+using namespace psp;
+
+namespace psp {
+int csr_create(int, int, long long, const int *, const int *, const double *, psp_mat **, bool);
+int sss_create(int, long long, const int *, const int *, const double *, const double *, psp_mat **);
+}
+
+extern "C" int psp_csr_create(int m, int n, int nnz, const int *ind, const int *col,
+                              const double *val, psp_mat **out) {
+  if (!out || !ind || (nnz > 0 && (!col || !val))) { set_error("psp_csr_create: NULL argument"); return PSP_ERR_ARG; }
+  PSP_TRY(ensure_init());
+  return csr_create(m, n, nnz, ind, col, val, out, false);
+}
+
+extern "C" int psp_sss_create(int n, int nnz, const int *ind, const int *col, const double *val,
+                              const double *diag, psp_mat **out) {
+  if (!out || !ind || (n > 0 && !diag) || (nnz > 0 && (!col || !val))) {
+    set_error("psp_sss_create: NULL argument");
+    return PSP_ERR_ARG;
+  }
+  PSP_TRY(ensure_init());
+  return sss_create(n, nnz, ind, col, val, diag, out);
+}
+
+extern "C" void psp_mat_destroy(psp_mat *A) {
+  if (!A) return;
+  if (A->transp) psp_mat_destroy(A->transp);
+  cudaFree(A->d_ind); cudaFree(A->d_col); cudaFree(A->d_val); cudaFree(A->d_blk);
+  cudaFree(A->d_lind); cudaFree(A->d_lcol); cudaFree(A->d_lval); cudaFree(A->d_diag);
+  cudaFree(A->d_x); cudaFree(A->d_y);
+  delete A;
+}
+
+extern "C" int psp_mat_info(const psp_mat *A, int *m, int *n, long long *nnz, int *kind) {
+  if (!A) { set_error("psp_mat_info: NULL matrix"); return PSP_ERR_ARG; }
+  if (m) *m = A->m;
+  if (n) *n = A->n;
+  if (nnz) *nnz = A->nnz;
+  if (kind) *kind = A->kind;
+  return PSP_OK;
+}
+
+extern "C" int psp_matvec_dev(psp_mat *A, int transp, const double *dx, double *dy) {
+  if (!A || !dx || !dy) { set_error("psp_matvec_dev: NULL argument"); return PSP_ERR_ARG; }
+  PSP_TRY(ensure_init());
+  const psp_mat *M = A;
+  if (transp && A->kind == 1) { PSP_TRY(mat_transpose(A)); M = A->transp; }
+  return spmv_launch(M, dx, dy, SpmvDots());
+}
+
+static int ensure_vec(double **p, size_t *cap, size_t n) {
+  if (*cap >= n && *p) return PSP_OK;
+  if (*p) cudaFree(*p);
+  *p = nullptr; *cap = 0;
+  cudaError_t e = cudaMalloc((void **)p, sizeof(double) * (n > 0 ? n : 1));
+  if (e != cudaSuccess) { set_error("cudaMalloc of a vector of %zu doubles failed", n); return PSP_ERR_NOMEM; }
+  *cap = n;
+  return PSP_OK;
+}
+
+extern "C" int psp_matvec(psp_mat *A, int transp, const double *x, long incx, double *y, long incy) {
+  if (!A || (!x && A->n) || (!y && A->m)) { set_error("psp_matvec: NULL argument"); return PSP_ERR_ARG; }
+  PSP_TRY(ensure_init());
+  Ctx &c = ctx();
+  const bool t = transp && A->kind == 1;
+  const size_t nx = t ? A->m : A->n, ny = t ? A->n : A->m;
+  PSP_TRY(ensure_vec(&A->d_x, &A->x_cap, nx));
+  PSP_TRY(ensure_vec(&A->d_y, &A->y_cap, ny));
+  PSP_TRY(psp_vec_upload(A->d_x, x, nx, incx));
+  PSP_CUDA(cudaEventRecord(c.ev0, c.stream));
+  PSP_TRY(psp_matvec_dev(A, transp, A->d_x, A->d_y));
+  PSP_CUDA(cudaEventRecord(c.ev1, c.stream));
+  PSP_TRY(psp_vec_download(A->d_y, y, ny, incy));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, c.ev0, c.ev1);
+  c.last_ms = ms;
+  return PSP_OK;
+}
