@@ -76,6 +76,7 @@ struct Ctx {
   long long launches = 0;
   // options
   long long spmv_variant = 0;
+  long long spmv_ctas = 0;    // cap on resident CTAs per SM for the TMA SpMV (0: occupancy limit)
   long long poll_chunk = 0;   // 0: automatic
   long long use_graph = 1;
 };

@@ -184,6 +184,7 @@ extern "C" int psp_set_option(const char *name, long long value) {
   if (!name) return PSP_ERR_ARG;
   Ctx &c = g_ctx;
   if (!strcmp(name, "spmv_variant")) c.spmv_variant = value;
+  else if (!strcmp(name, "spmv_ctas")) c.spmv_ctas = value;
   else if (!strcmp(name, "poll_chunk")) c.poll_chunk = value;
   else if (!strcmp(name, "use_graph")) c.use_graph = value;
   else { set_error("unknown option '%s'", name); return PSP_ERR_ARG; }
@@ -194,6 +195,7 @@ extern "C" long long psp_get_option(const char *name) {
   Ctx &c = g_ctx;
   if (!name) return -1;
   if (!strcmp(name, "spmv_variant")) return c.spmv_variant;
+  if (!strcmp(name, "spmv_ctas")) return c.spmv_ctas;
   if (!strcmp(name, "poll_chunk")) return c.poll_chunk;
   if (!strcmp(name, "use_graph")) return c.use_graph;
   if (!strcmp(name, "sms")) return c.sms;

@@ -69,8 +69,9 @@ __global__ void __launch_bounds__(kThreads, 4) k_spmv_stream(SpmvArgs a) {
   double acc0 = 0.0, acc1 = 0.0;
 
   for (int b = blockIdx.x; b < a.nb; b += gridDim.x) {
-    const int r0 = __ldg(a.blk + b), r1 = __ldg(a.blk + b + 1);
-    const int k0 = __ldg(a.ind + r0), k1 = __ldg(a.ind + r1);
+    const int2 d0 = __ldg(reinterpret_cast<const int2 *>(a.blk) + b);
+    const int2 d1 = __ldg(reinterpret_cast<const int2 *>(a.blk) + b + 1);
+    const int r0 = d0.x, r1 = d1.x, k0 = d0.y, k1 = d1.y;
     const int nrows = r1 - r0, cnt = k1 - k0;
 
     if (cnt <= kBlkNnz) {
@@ -165,6 +166,205 @@ __global__ void __launch_bounds__(kThreads, 4) k_spmv_stream(SpmvArgs a) {
   }
 }
 
+
+// ---------------------------------------------------------------- TMA-fed variant
+// Same row-block schedule and the same arithmetic, but the block's slices of
+// val / col / ind are brought into shared memory by the TMA unit
+// (cp.async.bulk, completion on an mbarrier) through a STAGES-deep ring, so
+// the streaming part of the traffic costs no LSU issue slots or registers and
+// the next blocks are in flight while the current one is reduced.  One thread
+// per row then walks its row in shared memory: consecutive lanes gather
+// x[col] for consecutive rows, which for banded matrices touches 2-3 cache
+// lines per warp instruction instead of one line per diagonal per few lanes.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+constexpr int kStageVal = 2048 * 8;                 // bytes
+constexpr int kStageCol = 2048 * 4;
+constexpr int kStageInd = 272 * 4;                  // kThreads + 1 rows, +3 alignment, rounded to 16 B
+constexpr int kStageBytes = kStageVal + kStageCol + kStageInd;   // 25664, multiple of 128
+
+template <int STAGES, bool DOTS>
+__global__ void __launch_bounds__(kThreads) k_spmv_tma(SpmvArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t full[STAGES];
+  __shared__ double red_sh[8];
+  if (DOTS) {
+    const volatile State *V = a.S;
+    if (V->done || (a.gate == 1 && V->cyc_done)) return;
+  }
+  const int tid = threadIdx.x;
+  const int2 *blk = reinterpret_cast<const int2 *>(a.blk);
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; s++) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // producer (thread 0): start the bulk copies of row block b into `stage`
+  auto issue = [&](int b, int stage) {
+    const int2 d0 = __ldg(blk + b), d1 = __ldg(blk + b + 1);
+    const int cnt = d1.y - d0.y;
+    if (cnt > kBlkNnz) return;                      // over-long row: read straight from global
+    const int base = d0.y & ~3, rbase = d0.x & ~3;
+    const uint32_t ne = (uint32_t)((d1.y - base + 3) & ~3);
+    const uint32_t nr = (uint32_t)((d1.x + 1 - rbase + 3) & ~3);
+    unsigned char *st = smem + (size_t)stage * kStageBytes;
+    mbar_expect_tx(&full[stage], ne * 12u + nr * 4u);
+    tma_load_1d(st, a.val + base, ne * 8u, &full[stage]);
+    tma_load_1d(st + kStageVal, a.col + base, ne * 4u, &full[stage]);
+    tma_load_1d(st + kStageVal + kStageCol, a.ind + rbase, nr * 4u, &full[stage]);
+  };
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; s++) {
+      const int b = blockIdx.x + s * gridDim.x;
+      if (b < a.nb) issue(b, s);
+    }
+  }
+
+  double acc0 = 0.0, acc1 = 0.0;
+  int it = 0;
+  uint32_t phases = 0;
+  for (int b = blockIdx.x; b < a.nb; b += gridDim.x, it++) {
+    const int stage = it % STAGES;
+    const uint32_t parity = (phases >> stage) & 1u;   // flips only when the stage was really used
+    const int2 d0 = __ldg(blk + b), d1 = __ldg(blk + b + 1);
+    const int r0 = d0.x, r1 = d1.x, k0 = d0.y, k1 = d1.y;
+    const int nrows = r1 - r0, cnt = k1 - k0;
+    if (cnt <= kBlkNnz) {
+      const unsigned char *st = smem + (size_t)stage * kStageBytes;
+      const double *sval = reinterpret_cast<const double *>(st);
+      const int *scol = reinterpret_cast<const int *>(st + kStageVal);
+      const int *sind = reinterpret_cast<const int *>(st + kStageVal + kStageCol);
+      const int base = k0 & ~3, roff = r0 - (r0 & ~3);
+      mbar_wait(&full[stage], parity);
+      phases ^= (1u << stage);
+      if (cnt <= 16 * nrows) {
+        if (tid < nrows) {
+          const int r = r0 + tid;
+          const int s = sind[roff + tid] - base, e = sind[roff + tid + 1] - base;
+          double sum = 0.0;
+          for (int k = s; k < e; k += 8) {
+            double pr[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+              pr[j] = (k + j < e) ? __dmul_rn(sval[k + j], ldg_f64(a.x + scol[k + j])) : 0.0;
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+              if (k + j < e) sum = __dadd_rn(sum, pr[j]);
+          }
+          a.y[r] = sum;
+          if (DOTS) {
+            if (a.w1) acc0 += a.w1[r] * sum;
+            if (a.w2_is_y) acc1 += sum * sum;
+            else if (a.w2) acc1 += a.w2[r] * sum;
+          }
+        }
+      } else {
+        const int w = tid >> 5, l = tid & 31;
+        for (int rr = w; rr < nrows; rr += kThreads / 32) {
+          const int r = r0 + rr;
+          const int s = sind[roff + rr] - base, e = sind[roff + rr + 1] - base;
+          double sum = 0.0;
+          for (int k = s + l; k < e; k += 32) sum += sval[k] * ldg_f64(a.x + scol[k]);
+          sum = warp_sum(sum);
+          if (l == 0) {
+            a.y[r] = sum;
+            if (DOTS) {
+              if (a.w1) acc0 += a.w1[r] * sum;
+              if (a.w2_is_y) acc1 += sum * sum;
+              else if (a.w2) acc1 += a.w2[r] * sum;
+            }
+          }
+        }
+      }
+    } else {
+      double sum = 0.0;
+      for (int k = k0 + tid; k < k1; k += kThreads)
+        sum += __ldg(a.val + k) * ldg_f64(a.x + __ldg(a.col + k));
+      sum = block_sum(sum, red_sh);
+      if (tid == 0) {
+        a.y[r0] = sum;
+        if (DOTS) {
+          if (a.w1) acc0 += a.w1[r0] * sum;
+          if (a.w2_is_y) acc1 += sum * sum;
+          else if (a.w2) acc1 += a.w2[r0] * sum;
+        }
+      }
+    }
+    __syncthreads();                                // everyone is done with this stage's buffers
+    if (tid == 0) {
+      const int nb2 = b + STAGES * gridDim.x;
+      if (nb2 < a.nb) issue(nb2, stage);
+    }
+  }
+
+  if (DOTS) {
+    double mine[2];
+    mine[0] = block_sum(acc0, red_sh);
+    mine[1] = block_sum(acc1, red_sh);
+    double tot[2], dummy;
+    if (grid_reduce_finish<2, false>(mine, 0.0, a.partials, a.ticket, tot, &dummy, red_sh)) {
+      if (tid == 0) {
+        a.S->red[0] = tot[0];
+        a.S->red[1] = tot[1];
+        run_epilogue(a.epilogue, a.S, a.aux);
+      }
+    }
+  }
+}
+
+template <int STAGES, bool DOTS>
+static int launch_tma(const SpmvArgs &a, int nb, int ctas_per_sm) {
+  Ctx &c = ctx();
+  static int resident = 0, cached_cap = -1;
+  const int smem_bytes = STAGES * kStageBytes;
+  if (resident == 0 || cached_cap != ctas_per_sm) {
+    cached_cap = ctas_per_sm;
+    PSP_CUDA(cudaFuncSetAttribute(k_spmv_tma<STAGES, DOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_spmv_tma<STAGES, DOTS>, kThreads, smem_bytes) != cudaSuccess || per_sm < 1)
+      per_sm = 1;
+    if (ctas_per_sm > 0 && per_sm > ctas_per_sm) per_sm = ctas_per_sm;
+    resident = per_sm * c.sms;
+    if (resident > kMaxGrid) resident = kMaxGrid;
+  }
+  const int grid = nb < resident ? nb : resident;
+  k_spmv_tma<STAGES, DOTS><<<grid, kThreads, smem_bytes, c.stream>>>(a);
+  PSP_LAUNCH_CHECK();
+  return PSP_OK;
+}
+
 // ---------------------------------------------------------------- host side
 
 static int upload(const void *src, size_t bytes, void **dst, size_t pad_bytes = 64) {
@@ -214,9 +414,11 @@ static int check_csr(int m, int n, long long nnz, const int *ind, const int *col
 }
 
 static int finish_csr_upload(psp_mat *A, const std::vector<int> &ind, const int *col, const double *val) {
-  std::vector<int> blk;
-  build_row_blocks(A->m, ind.data(), blk);
-  A->nb = (int)blk.size() - 1;
+  std::vector<int> rows, blk;
+  build_row_blocks(A->m, ind.data(), rows);
+  A->nb = (int)rows.size() - 1;
+  blk.resize(2 * rows.size());          // (first row, first entry) per block + sentinel
+  for (size_t i = 0; i < rows.size(); i++) { blk[2 * i] = rows[i]; blk[2 * i + 1] = ind[rows[i]]; }
   PSP_TRY(upload(ind.data(), sizeof(int) * (size_t)(A->m + 1), (void **)&A->d_ind));
   PSP_TRY(upload(col, sizeof(int) * (size_t)A->fnnz, (void **)&A->d_col));
   PSP_TRY(upload(val, sizeof(double) * (size_t)A->fnnz, (void **)&A->d_val));
@@ -324,13 +526,28 @@ int spmv_launch(const psp_mat *A, const double *dx, double *dy, const SpmvDots &
   a.w1 = d.w1; a.w2 = d.w2; a.w2_is_y = d.w2_is_y; a.epilogue = d.epilogue; a.S = d.S;
   a.gate = d.gate;
   a.partials = c.partials; a.ticket = c.tickets; a.aux = nullptr;
-  int grid = A->nb;
-  int cap = c.sms * 6;
-  if (cap > kMaxGrid) cap = kMaxGrid;
-  if (grid > cap) grid = cap;
+  if (d.S) a.aux = (void *)(d.S + 1);   // solver-specific small state sits right behind the State
+  if (c.spmv_variant == 3 || c.spmv_variant == 0) {
+    return d.S ? launch_tma<2, true>(a, A->nb, (int)c.spmv_ctas) : launch_tma<2, false>(a, A->nb, (int)c.spmv_ctas);
+  }
+  if (c.spmv_variant == 4) {
+    return d.S ? launch_tma<3, true>(a, A->nb, (int)c.spmv_ctas) : launch_tma<3, false>(a, A->nb, (int)c.spmv_ctas);
+  }
   const bool vec = (c.spmv_variant != 1);
+  // persistent grid: exactly the number of CTAs that are resident at once
+  static int resident[2][2] = {{0, 0}, {0, 0}};
+  int &res = resident[vec ? 1 : 0][d.S ? 1 : 0];
+  if (res == 0) {
+    const void *fn = vec ? (d.S ? (const void *)k_spmv_stream<1, true> : (const void *)k_spmv_stream<1, false>)
+                         : (d.S ? (const void *)k_spmv_stream<0, true> : (const void *)k_spmv_stream<0, false>);
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, 0) != cudaSuccess || per_sm < 1)
+      per_sm = 1;
+    res = per_sm * c.sms;
+    if (res > kMaxGrid) res = kMaxGrid;
+  }
+  int grid = A->nb < res ? A->nb : res;
   if (d.S) {
-    a.aux = (void *)(d.S + 1);   // solver-specific small state sits right behind the State
     if (vec) k_spmv_stream<1, true><<<grid, kThreads, 0, c.stream>>>(a);
     else k_spmv_stream<0, true><<<grid, kThreads, 0, c.stream>>>(a);
   } else {

@@ -38,7 +38,7 @@ for name, mat in [("p2d_37", g.poisson2d(37)), ("p3d_24", g.poisson3d(24)), ("cd
     n = mat["n"]
     shape = mat.get("shape", (n, n))
     val, col, ind = mat["csr"]
-    for variant in (1, 2):
+    for variant in (1, 2, 3, 4):
         P.set_option("spmv_variant", variant)
         A = P.Matrix.csr(shape[0], shape[1], val, col, ind)
         Ao = ora.csr(shape[0], shape[1], val, col, ind)
