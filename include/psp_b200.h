@@ -172,6 +172,17 @@ int psp_solve_dev(int solver, const psp_operator *A, const psp_operator *K, int 
  * psp_matvec call, measured with CUDA events on the library stream (ms). */
 double psp_last_device_ms(void);
 
+/* Timing helpers on the library stream (the stream every kernel of this
+ * library is launched on): record one of 8 CUDA events / elapsed ms between
+ * two recorded events (synchronises on `stop`). */
+int psp_event_record(int idx);
+int psp_event_elapsed_ms(int start, int stop, double *ms);
+
+/* Sampled SpMV kernel timing: returns the number of SpMV launches bracketed by
+ * event pairs since the last call and their summed duration, then re-arms
+ * sampling to every `sample_every`-th SpMV launch (0 = off, the default). */
+int psp_spmv_timing(int sample_every, int *count, double *total_ms);
+
 /* ---- tuning knobs (default to reference semantics) --------------------- */
 /* name: "spmv_variant" (0 auto, 1 scalar-stream, 2 vector-stream ...),
  *       "poll_chunk" (iterations enqueued between convergence polls),

@@ -28,6 +28,7 @@ SYMBOLS = [
     "psp_jacobi_create", "psp_ssor_create", "psp_prec_destroy", "psp_prec_apply",
     "psp_prec_apply_dev", "psp_ssor_levels",
     "psp_solve", "psp_solve_dev", "psp_last_device_ms", "psp_set_option", "psp_get_option",
+    "psp_event_record", "psp_event_elapsed_ms", "psp_spmv_timing",
 ]
 
 SOLVERS = {"pcg": 0, "minres": 1, "qmrs": 2, "bicgstab": 3, "cgs": 4, "gmres": 5}
@@ -82,6 +83,9 @@ def _load():
     L.psp_prec_apply.argtypes = [C.c_void_p, _dp, _dp]
     L.psp_prec_apply_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.psp_ssor_levels.argtypes = [C.c_void_p, _ip, _ip, _ip, _ip]
+    L.psp_event_record.argtypes = [C.c_int]
+    L.psp_event_elapsed_ms.argtypes = [C.c_int, C.c_int, _dp]
+    L.psp_spmv_timing.argtypes = [C.c_int, _ip, _dp]
     for name in ("psp_solve", "psp_solve_dev"):
         getattr(L, name).argtypes = [C.c_int, C.POINTER(Operator), C.POINTER(Operator), C.c_int,
                                      C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int,
@@ -298,6 +302,23 @@ def last_device_ms() -> float:
 
 def launch_count(reset=False) -> int:
     return lib.psp_launch_count(int(reset))
+
+
+def event_record(idx: int) -> None:
+    check(lib.psp_event_record(idx))
+
+
+def event_elapsed_ms(start: int, stop: int) -> float:
+    ms = C.c_double()
+    check(lib.psp_event_elapsed_ms(start, stop, C.byref(ms)))
+    return ms.value
+
+
+def spmv_timing(sample_every: int = 0):
+    """(count, total_ms) of the sampled SpMV launches since the last call; re-arms sampling."""
+    cnt, ms = C.c_int(), C.c_double()
+    check(lib.psp_spmv_timing(sample_every, C.byref(cnt), C.byref(ms)))
+    return cnt.value, ms.value
 
 
 def set_option(name: str, value: int) -> None:

@@ -79,6 +79,13 @@ struct Ctx {
   long long spmv_ctas = 0;    // cap on resident CTAs per SM for the TMA SpMV (0: occupancy limit)
   long long poll_chunk = 0;   // 0: automatic
   long long use_graph = 1;
+  // sampled SpMV timing (bench.py roofline): event pairs around every Nth launch
+  static constexpr int kSpmvPairs = 512;
+  long long spmv_sample = 0, spmv_seen = 0;
+  int spmv_pairs = 0;
+  cudaEvent_t spmv_ev[2 * kSpmvPairs] = {};
+  // general-purpose timing events on the library stream (psp_event_record)
+  cudaEvent_t user_ev[8] = {};
 };
 
 Ctx &ctx();

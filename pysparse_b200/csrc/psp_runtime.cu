@@ -180,6 +180,44 @@ extern "C" int psp_vec_fill(double *dptr, size_t n, double value) {
   return PSP_OK;
 }
 
+extern "C" int psp_event_record(int idx) {
+  if (idx < 0 || idx >= 8) { set_error("psp_event_record: index out of range"); return PSP_ERR_ARG; }
+  PSP_TRY(ensure_init());
+  if (!g_ctx.user_ev[idx]) PSP_CUDA(cudaEventCreate(&g_ctx.user_ev[idx]));
+  PSP_CUDA(cudaEventRecord(g_ctx.user_ev[idx], g_ctx.stream));
+  return PSP_OK;
+}
+
+extern "C" int psp_event_elapsed_ms(int start, int stop, double *ms) {
+  if (start < 0 || start >= 8 || stop < 0 || stop >= 8 || !ms || !g_ctx.user_ev[start] || !g_ctx.user_ev[stop]) {
+    set_error("psp_event_elapsed_ms: bad arguments");
+    return PSP_ERR_ARG;
+  }
+  PSP_CUDA(cudaEventSynchronize(g_ctx.user_ev[stop]));
+  float f = 0.f;
+  PSP_CUDA(cudaEventElapsedTime(&f, g_ctx.user_ev[start], g_ctx.user_ev[stop]));
+  *ms = f;
+  return PSP_OK;
+}
+
+extern "C" int psp_spmv_timing(int sample_every, int *count, double *total_ms) {
+  PSP_TRY(ensure_init());
+  Ctx &c = g_ctx;
+  PSP_CUDA(cudaStreamSynchronize(c.stream));
+  double tot = 0.0;
+  for (int i = 0; i < c.spmv_pairs; i++) {
+    float f = 0.f;
+    PSP_CUDA(cudaEventElapsedTime(&f, c.spmv_ev[2 * i], c.spmv_ev[2 * i + 1]));
+    tot += f;
+  }
+  if (count) *count = c.spmv_pairs;
+  if (total_ms) *total_ms = tot;
+  c.spmv_pairs = 0;
+  c.spmv_seen = 0;
+  c.spmv_sample = sample_every;
+  return PSP_OK;
+}
+
 extern "C" int psp_set_option(const char *name, long long value) {
   if (!name) return PSP_ERR_ARG;
   Ctx &c = g_ctx;

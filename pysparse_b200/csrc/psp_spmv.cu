@@ -517,9 +517,32 @@ int mat_transpose(psp_mat *A) {
   return PSP_OK;
 }
 
+static int spmv_dispatch(const psp_mat *A, const double *dx, double *dy, const SpmvDots &d);
+
+// Every `spmv_sample`-th SpMV launch is bracketed by a CUDA-event pair on the
+// library stream (bench.py's live roofline measurement: the kernel is timed
+// where it runs, inside the solver loop).  Off by default.
 int spmv_launch(const psp_mat *A, const double *dx, double *dy, const SpmvDots &d) {
   Ctx &c = ctx();
   if (A->m == 0) return PSP_OK;
+  bool sample = false;
+  if (c.spmv_sample > 0) {
+    sample = (c.spmv_seen % c.spmv_sample == 0) && c.spmv_pairs < Ctx::kSpmvPairs;
+    c.spmv_seen++;
+  }
+  if (!sample) return spmv_dispatch(A, dx, dy, d);
+  if (!c.spmv_ev[0]) {
+    for (int i = 0; i < 2 * Ctx::kSpmvPairs; i++) PSP_CUDA(cudaEventCreate(&c.spmv_ev[i]));
+  }
+  PSP_CUDA(cudaEventRecord(c.spmv_ev[2 * c.spmv_pairs], c.stream));
+  PSP_TRY(spmv_dispatch(A, dx, dy, d));
+  PSP_CUDA(cudaEventRecord(c.spmv_ev[2 * c.spmv_pairs + 1], c.stream));
+  c.spmv_pairs++;
+  return PSP_OK;
+}
+
+static int spmv_dispatch(const psp_mat *A, const double *dx, double *dy, const SpmvDots &d) {
+  Ctx &c = ctx();
   SpmvArgs a;
   a.ind = A->d_ind; a.col = A->d_col; a.blk = A->d_blk; a.val = A->d_val;
   a.x = dx; a.y = dy; a.nb = A->nb;

@@ -1,0 +1,53 @@
+"""CPU tests of the C-ABI boundary: the library builds for sm_100a, loads, exports
+every symbol include/psp_b200.h declares, and refuses to compute without a GPU
+(no CPU fallback)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "psp_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(psp_[a-z0-9_]+)\s*\(", text)) - {"psp_callback"})
+
+
+def test_header_symbols_are_exported(native):
+    lib = ctypes.CDLL(native.LIB_PATH)
+    syms = declared_symbols()
+    assert len(syms) >= 30
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in psp_b200.h but not exported"
+    assert sorted(native.SYMBOLS) == syms
+
+
+def test_library_contains_sm100a_code_and_tma(native):
+    out = subprocess.run(["cuobjdump", "-lelf", native.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    sass = subprocess.run(["cuobjdump", "-sass", native.LIB_PATH], capture_output=True, text=True).stdout
+    assert "UBLKCP" in sass          # cp.async.bulk (TMA) feeding the SpMV
+
+
+def test_no_cpu_fallback(native):
+    if native.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(native.PspError) as e:
+        native.Matrix.csr(1, 1, [1.0], [0], [0, 1])
+    assert e.value.status == -1      # PSP_ERR_NO_DEVICE
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_oracle_is_not_imported_by_the_product():
+    import pysparse_b200  # noqa: F401
+    pkg = os.path.join(ROOT, "pysparse_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".c", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "import oracle" not in src and "from oracle" not in src and "psp_oracle" not in src, f

@@ -1,0 +1,198 @@
+"""GPU parity tests (pytest -m gpu): the CUDA path, called through the C-ABI,
+against the CPU oracle and the committed golden fixtures.
+
+Contract (BASELINE.json north_star):
+  * SpMV: relative max-norm error <= 1e-13 (short-row paths are in fact
+    bit-identical to the reference because they keep its accumulation order);
+  * solvers: same flag, iteration count within +-2 %, relres within 1e-10;
+  * structure work (level sets, transposes): bit-exact.
+"""
+import numpy as np
+import pytest
+
+from cases import KERNEL_CASES, SOLVER_CASES, build_matrix, make_ops
+from helpers import GpuLib, load_kat, load_kernels, relmax, start_vectors
+
+pytestmark = pytest.mark.gpu
+
+SPMV_TOL = 1e-13       # north_star: relative max-norm error of SpMV
+RELRES_TOL = 1e-10     # north_star: final relative residual within 1e-10 of the reference
+ITER_TOL = 0.02        # north_star: iteration count within +-2 %
+KAT = {r["id"]: r for r in load_kat()}
+
+
+@pytest.fixture(scope="module")
+def gpu(native):
+    if native.device_count() == 0:
+        pytest.fail("no CUDA device: GPU tests must run on the B200 box")
+    return GpuLib(native)
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
+@pytest.mark.parametrize("kc", KERNEL_CASES, ids=lambda c: c["id"])
+def test_spmv_and_precon_kernels_vs_golden(gpu, native, kc, variant):
+    native.set_option("spmv_variant", variant)
+    try:
+        G = load_kernels()
+        mat = build_matrix(kc["matrix"])
+        n = mat["n"]
+        shape = mat.get("shape", (n, n))
+        rng = np.random.default_rng(kc["seed"])
+        x = rng.standard_normal(shape[1])
+        xt = rng.standard_normal(shape[0])
+        key = kc["id"]
+        A = gpu.csr(shape[0], shape[1], *mat["csr"])
+        y = np.full(shape[0], np.nan); gpu.matvec(A, x, y)
+        assert relmax(y, G[key + "/csr_y"]) <= SPMV_TOL
+        yt = np.full(shape[1], np.nan); gpu.matvec(A, xt, yt, transp=True)
+        assert relmax(yt, G[key + "/csr_yt"]) <= SPMV_TOL
+        if key not in ("pow_3000",):     # short rows keep the reference's summation order
+            assert np.array_equal(y, G[key + "/csr_y"]) and np.array_equal(yt, G[key + "/csr_yt"])
+        if "sss" in mat:
+            S = gpu.sss(n, *mat["sss"])
+            ys = np.full(n, np.nan); gpu.matvec(S, x, ys)
+            assert relmax(ys, G[key + "/sss_y"]) <= SPMV_TOL
+            yst = np.full(n, np.nan); gpu.matvec(S, x, yst, transp=True)   # matvec_transp aliased (sss_mat.c:108)
+            assert np.array_equal(ys, yst)
+            for om, st in kc.get("ssor", []):
+                z = np.full(n, np.nan); gpu.precon(gpu.ssor(S, om, st), x, z)
+                assert relmax(z, G[f"{key}/ssor_{om}_{st}"]) <= SPMV_TOL
+            for om, st in kc.get("jacobi", []):
+                z = np.full(n, np.nan); gpu.precon(gpu.jacobi(S, mat["sss"][1], om, st), x, z)
+                assert relmax(z, G[f"{key}/jacobi_{om}_{st}"]) <= SPMV_TOL
+    finally:
+        native.set_option("spmv_variant", 0)
+
+
+def test_spmv_strided_views(gpu, checker):
+    mat = build_matrix(["convdiff3d", 9])
+    n = mat["n"]
+    A = gpu.csr(n, n, *mat["csr"]); Ao = checker.csr(n, n, *mat["csr"])
+    rng = np.random.default_rng(3)
+    xs = rng.standard_normal(3 * n)[::3]
+    ys = np.zeros(2 * n)[::2]; yo = np.zeros(2 * n)[::2]
+    gpu.matvec(A, xs, ys); checker.matvec(Ao, xs, yo)
+    assert np.array_equal(ys, yo)
+    gpu.matvec(A, xs, ys, transp=True); checker.matvec(Ao, xs, yo, transp=True)
+    assert np.array_equal(ys, yo)
+
+
+@pytest.mark.parametrize("case", SOLVER_CASES, ids=lambda c: c["id"])
+def test_solvers_vs_golden_and_oracle(gpu, checker, case):
+    mat = build_matrix(case["matrix"])
+    n = mat["n"]
+    A, K = make_ops(gpu, mat, case)
+    b, x = start_vectors(case, n)
+    info, it, rr = gpu.solve(case["solver"], A, b, x, case["tol"], case["maxit"], K, case.get("dim", 20))
+    g = KAT[case["id"]]
+    assert info == g["info"], (info, it, rr, g)
+    if np.isnan(g["relres"]):
+        assert np.isnan(rr)
+    elif g["info"] == 0 or case.get("stable", False):
+        if case.get("stable", False):
+            assert abs(it - g["iter"]) <= max(1, int(ITER_TOL * g["iter"])), (it, g["iter"])
+            if g["info"] == 0 or g["relres"] < 1e3:
+                assert abs(rr - g["relres"]) <= max(RELRES_TOL, 1e-6 * abs(g["relres"])), (rr, g["relres"])
+        else:
+            # rounding-chaotic case: converged below tol like the reference
+            assert rr < case["tol"] and abs(it - g["iter"]) <= 0.35 * g["iter"]
+    if g["info"] == 0:
+        # same solution as the reference to solver accuracy
+        Ao, Ko = make_ops(checker, mat, case)
+        bo, xo = start_vectors(case, n)
+        checker.solve(case["solver"], Ao, bo, xo, case["tol"], case["maxit"], Ko, case.get("dim", 20))
+        scale = max(1.0, float(np.max(np.abs(xo))))
+        assert float(np.max(np.abs(x - xo))) <= 50 * case["tol"] * scale * max(1.0, n ** 0.5) + 1e-9 * scale
+
+
+def test_ssor_level_sets_bit_exact(gpu):
+    """Level sets of L / L^T against a direct Python restatement of the recurrence."""
+    mat = build_matrix(["random_sym", 3000, 7, 4])
+    n = mat["n"]
+    val, diag, col, ind = mat["sss"]
+    S = gpu.sss(n, val, diag, col, ind)
+    K = gpu.ssor(S, 1.0, 1)
+    nf, nb, lf, lb = K.levels()
+    ef = np.zeros(n, dtype=np.int32)
+    for i in range(n):
+        c = col[ind[i]:ind[i + 1]]
+        ef[i] = ef[c].max() + 1 if len(c) else 0
+    eb = np.zeros(n, dtype=np.int32)
+    for i in range(n - 1, -1, -1):
+        for j in col[ind[i]:ind[i + 1]]:
+            eb[j] = max(eb[j], eb[i] + 1)
+    assert np.array_equal(lf, ef) and np.array_equal(lb, eb)
+    assert nf == ef.max() + 1 and nb == eb.max() + 1
+    # 2-D lexicographic grid: 2n-1 wavefronts
+    m2 = build_matrix(["poisson2d", 23])
+    K2 = gpu.ssor(gpu.sss(m2["n"], *m2["sss"]))
+    assert K2.levels()[:2] == (45, 45)
+
+
+def test_foreign_operator_callbacks(gpu, native, checker):
+    """A and K given as duck-typed Python objects (host-staged callback path)."""
+    mat = build_matrix(["poisson2d", 40])
+    n = mat["n"]
+    A = gpu.csr(n, n, *mat["csr"])
+    Ao = checker.csr(n, n, *mat["csr"])
+
+    class PyMat:
+        shape = (n, n)
+        calls = 0
+
+        def matvec(self, x, y):
+            PyMat.calls += 1
+            checker.matvec(Ao, x, y)
+
+    class PyPrec:
+        shape = (n, n)
+
+        def precon(self, x, y):
+            y[:] = x / 4.0
+
+    for solver in ("pcg", "minres", "qmrs", "bicgstab", "cgs", "gmres"):
+        x1 = np.zeros(n); x2 = np.zeros(n)
+        r1 = native.solve(solver, A, np.ones(n), x1, 1e-8, 500, native.Precon.jacobi(A, np.full(n, 4.0)))
+        r2 = native.solve(solver, PyMat(), np.ones(n), x2, 1e-8, 500, PyPrec())
+        assert r1[0] == r2[0] == 0
+        assert abs(r1[1] - r2[1]) <= max(1, 0.1 * r1[1])
+        assert np.max(np.abs(x1 - x2)) <= 1e-6 * np.max(np.abs(x1))
+
+    class Boom:
+        shape = (n, n)
+
+        def matvec(self, x, y):
+            raise ValueError("boom")
+
+    with pytest.raises(ValueError):
+        native.solve("pcg", Boom(), np.ones(n), np.zeros(n), 1e-8, 10)
+
+
+def test_device_resident_solve_and_launch_counter(native):
+    mat = build_matrix(["poisson3d", 20])
+    n = mat["n"]
+    S = native.Matrix.sss(n, *mat["sss"])
+    K = native.Precon.jacobi(S, mat["sss"][1])
+    db = native.DeviceVector(n, np.ones(n)); dx = native.DeviceVector(n, np.zeros(n))
+    native.launch_count(reset=True)
+    r = native.solve("pcg", S, db, dx, 1e-10, 1000, K, dev=True)
+    assert r[0] == 0 and native.launch_count() >= 3 * r[1]
+    x = dx.download()
+    y = np.zeros(n); S.matvec(x, y)
+    assert np.linalg.norm(1.0 - y) / np.sqrt(n) <= 1e-9
+
+
+@pytest.mark.parametrize("nn", [96])
+def test_full_size_properties(native, nn):
+    """Size-independent properties at a larger size: linearity of the SpMV, symmetry
+    x'(Ay) == y'(Ax), SSS == CSR, transposed == direct for a symmetric matrix."""
+    mat = build_matrix(["poisson3d", nn])
+    n = mat["n"]
+    A = native.Matrix.csr(n, n, *mat["csr"]); S = native.Matrix.sss(n, *mat["sss"])
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(n); z = rng.standard_normal(n)
+    ax = np.empty(n); az = np.empty(n); axz = np.empty(n); sx = np.empty(n); atx = np.empty(n)
+    A.matvec(x, ax); A.matvec(z, az); A.matvec(x + 2.0 * z, axz); S.matvec(x, sx); A.matvec(x, atx, transp=True)
+    assert relmax(axz, ax + 2.0 * az) <= 1e-13
+    assert np.array_equal(ax, sx) and np.array_equal(ax, atx)
+    assert abs(z @ ax - x @ az) <= 1e-10 * abs(z @ ax)
