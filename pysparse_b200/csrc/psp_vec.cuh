@@ -62,7 +62,14 @@ __global__ void __launch_bounds__(kThreads) k_map(F f, long n, State *S, double 
 template <class F>
 inline int launch_map(const F &f, long n, int epilogue = EPI_NONE, int gate = 0) {
   Ctx &c = ctx();
-  int grid = grid_for((size_t)(n > 0 ? n : 1));
+  // persistent grid = exactly the CTAs of this instantiation that are resident at once
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_map<F>, kThreads, 0) != cudaSuccess || per_sm < 1)
+      per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+  }
+  int grid = grid_for((size_t)(n > 0 ? n : 1), per_sm);
   k_map<F><<<grid, kThreads, 0, c.stream>>>(f, n, c.state, c.partials, c.tickets, epilogue, gate);
   PSP_LAUNCH_CHECK();
   return PSP_OK;

@@ -1,0 +1,1189 @@
+/* spmatrixmodule.c -- module `spmatrix` of pysparse_b200: ll_mat / csr_mat /
+ * sss_mat types, the `_C_API` table, host-side structure conversion.
+ *
+ * Mirrors pysparse/sparse/src/spmatrixmodule.c (module functions :317-357, C-API
+ * :86-307), csr_mat.c (methods :114-171, attributes :208-231), sss_mat.c
+ * (:78-110, :149-172) and the parts of ll_mat.c users reach the hot path through
+ * (get/set :210-457, to_csr :1577-1648, to_sss :1654-1708, matvec :1434-1465,
+ * put, find, keys/values/items, copy, scale, shift, norm, generalize, compress).
+ *
+ * All products are computed on the GPU through include/psp_b200.h; the
+ * conversion routines are integer/structure work done on the host and are
+ * required to be bit-exact w.r.t. the reference's output arrays.
+ */
+#define PY_ARRAY_UNIQUE_SYMBOL psp_spmatrix_ARRAY_API
+#include "psp_host.h"
+#include <math.h>
+
+static PyTypeObject LLMatType, CSRMatType, SSSMatType;
+static PyObject *SpMatrix_ErrorObject;
+
+/* ------------------------------------------------------------------------- */
+/* argument checking of matvec-like calls (include/spmatrix.h:38-54)           */
+/* ------------------------------------------------------------------------- */
+static int parse_vec_pair(PyObject *args, PyArrayObject **x, PyArrayObject **y, long n1, long n2, int contiguous)
+{
+  if (!PyArg_ParseTuple(args, "O!O!", &PyArray_Type, x, &PyArray_Type, y)) return -1;
+  PyArrayObject *a[2] = {*x, *y};
+  long want[2] = {n1, n2};
+  for (int k = 0; k < 2; k++) {
+    if (PyArray_NDIM(a[k]) != 1 || PyArray_TYPE(a[k]) != NPY_DOUBLE || PyArray_DIM(a[k], 0) != want[k] ||
+        (contiguous && !PyArray_IS_C_CONTIGUOUS(a[k]))) {
+      PyErr_Format(PyExc_ValueError, contiguous
+                   ? "arg %d must be a contiguous 1-dimensional double array of appropriate size."
+                   : "arg %d must be a 1-dimensional double array of appropriate size.", k + 1);
+      return -1;
+    }
+  }
+  return 0;
+}
+
+static long elem_stride(PyArrayObject *a)
+{
+  return PyArray_DIM(a, 0) > 1 ? (long)(PyArray_STRIDE(a, 0) / (npy_intp)sizeof(double)) : 1;
+}
+
+static PyObject *device_matvec(psp_mat *dev, int transp, PyArrayObject *x, PyArrayObject *y)
+{
+  long incx = elem_stride(x), incy = elem_stride(y);
+  if (incx < 1 || incy < 1) {
+    PyErr_SetString(PyExc_ValueError, "negative strides are not supported");
+    return NULL;
+  }
+  int st = psp_matvec(dev, transp, (const double *)PyArray_DATA(x), incx, (double *)PyArray_DATA(y), incy);
+  if (st != PSP_OK) return psp_raise(st);
+  Py_RETURN_NONE;
+}
+
+static void mat_capsule_noop(PyObject *cap) { (void)cap; }
+
+/* ========================================================================= */
+/* csr_mat                                                                     */
+/* ========================================================================= */
+static PyObject *newCSRMatObject(int dim[], int nnz)
+{
+  CSRMatObject *op = PyObject_New(CSRMatObject, &CSRMatType);
+  if (!op) return PyErr_NoMemory();
+  op->dim[0] = dim[0]; op->dim[1] = dim[1]; op->nnz = nnz;
+  op->dev = NULL; op->base[0] = op->base[1] = op->base[2] = NULL;
+  op->val = PyMem_New(double, nnz > 0 ? nnz : 1);
+  op->col = PyMem_New(int, nnz > 0 ? nnz : 1);
+  op->ind = PyMem_New(int, dim[0] + 1);
+  if (!op->val || !op->col || !op->ind) {
+    PyMem_Free(op->val); PyMem_Free(op->col); PyMem_Free(op->ind);
+    PyObject_Del(op);
+    return PyErr_NoMemory();
+  }
+  return (PyObject *)op;
+}
+
+static psp_mat *csr_device(CSRMatObject *self)
+{
+  if (!self->dev) {
+    int st = psp_csr_create(self->dim[0], self->dim[1], self->nnz, self->ind, self->col, self->val, &self->dev);
+    if (st != PSP_OK) { psp_raise(st); return NULL; }
+  }
+  return self->dev;
+}
+
+static void CSRMat_dealloc(CSRMatObject *self)
+{
+  if (self->dev) psp_mat_destroy(self->dev);
+  if (self->base[0]) { Py_XDECREF(self->base[0]); Py_XDECREF(self->base[1]); Py_XDECREF(self->base[2]); }
+  else { PyMem_Free(self->val); PyMem_Free(self->col); PyMem_Free(self->ind); }
+  PyObject_Del(self);
+}
+
+static PyObject *CSRMat_matvec(CSRMatObject *self, PyObject *args)
+{
+  PyArrayObject *x, *y;
+  if (parse_vec_pair(args, &x, &y, self->dim[1], self->dim[0], 0)) return NULL;
+  psp_mat *d = csr_device(self);
+  return d ? device_matvec(d, 0, x, y) : NULL;
+}
+
+static PyObject *CSRMat_matvec_transp(CSRMatObject *self, PyObject *args)
+{
+  PyArrayObject *x, *y;
+  if (parse_vec_pair(args, &x, &y, self->dim[0], self->dim[1], 0)) return NULL;
+  psp_mat *d = csr_device(self);
+  return d ? device_matvec(d, 1, x, y) : NULL;
+}
+
+static PyObject *CSRMat_get_shape(CSRMatObject *self, void *c) { return Py_BuildValue("(i,i)", self->dim[0], self->dim[1]); }
+static PyObject *CSRMat_get_nnz(CSRMatObject *self, void *c) { return PyLong_FromLong(self->nnz); }
+static PyObject *CSRMat_get_dev(CSRMatObject *self, void *c)
+{
+  psp_mat *d = csr_device(self);
+  return d ? PyCapsule_New(d, PSP_MAT_CAPSULE, mat_capsule_noop) : NULL;
+}
+
+static PyObject *wrap_i32(int *p, npy_intp n, PyObject *owner)
+{
+  PyObject *a = PyArray_SimpleNewFromData(1, &n, NPY_INT32, p);
+  if (a) { Py_INCREF(owner); PyArray_SetBaseObject((PyArrayObject *)a, owner); PyArray_CLEARFLAGS((PyArrayObject *)a, NPY_ARRAY_WRITEABLE); }
+  return a;
+}
+static PyObject *wrap_f64(double *p, npy_intp n, PyObject *owner)
+{
+  PyObject *a = PyArray_SimpleNewFromData(1, &n, NPY_DOUBLE, p);
+  if (a) { Py_INCREF(owner); PyArray_SetBaseObject((PyArrayObject *)a, owner); PyArray_CLEARFLAGS((PyArrayObject *)a, NPY_ARRAY_WRITEABLE); }
+  return a;
+}
+
+/* read-only views of the storage arrays (pysparse_b200 addition; used by the
+ * bit-exactness tests of the conversions) */
+static PyObject *CSRMat_arrays(CSRMatObject *self, PyObject *noargs)
+{
+  return Py_BuildValue("(NNN)", wrap_f64(self->val, self->nnz, (PyObject *)self),
+                       wrap_i32(self->col, self->nnz, (PyObject *)self),
+                       wrap_i32(self->ind, self->dim[0] + 1, (PyObject *)self));
+}
+
+static PyObject *CSRMat_diagonal(CSRMatObject *self, PyObject *noargs);
+
+static PyMethodDef CSRMat_methods[] = {
+  {"matvec", (PyCFunction)CSRMat_matvec, METH_VARARGS, "a.matvec(x, y)\n\ncompute the sparse matrix-vector product y := a * x."},
+  {"matvec_transp", (PyCFunction)CSRMat_matvec_transp, METH_VARARGS, "a.matvec_transp(x, y)\n\ncompute the sparse matrix-vector product y := a^T * x."},
+  {"arrays", (PyCFunction)CSRMat_arrays, METH_NOARGS, "(val, col, ind) read-only views of the CSR storage"},
+  {"diagonal", (PyCFunction)CSRMat_diagonal, METH_NOARGS, "dense copy of the diagonal"},
+  {NULL, NULL}
+};
+static PyGetSetDef CSRMat_getset[] = {
+  {"shape", (getter)CSRMat_get_shape, NULL, NULL, NULL},
+  {"nnz", (getter)CSRMat_get_nnz, NULL, NULL, NULL},
+  {"_psp_mat", (getter)CSRMat_get_dev, NULL, "device handle (PyCapsule)", NULL},
+  {NULL}
+};
+
+static double csr_get(CSRMatObject *self, int i, int j)
+{
+  for (int k = self->ind[i]; k < self->ind[i + 1]; k++)
+    if (self->col[k] == j) return self->val[k];
+  return 0.0;
+}
+
+static PyObject *CSRMat_diagonal(CSRMatObject *self, PyObject *noargs)
+{
+  npy_intp n = self->dim[0] < self->dim[1] ? self->dim[0] : self->dim[1];
+  PyObject *a = PyArray_SimpleNew(1, &n, NPY_DOUBLE);
+  if (!a) return NULL;
+  double *d = (double *)PyArray_DATA((PyArrayObject *)a);
+  for (int i = 0; i < n; i++) d[i] = csr_get(self, i, i);
+  return a;
+}
+
+/* ========================================================================= */
+/* sss_mat                                                                     */
+/* ========================================================================= */
+static PyObject *newSSSMatObject(int n, int nnz)
+{
+  SSSMatObject *op = PyObject_New(SSSMatObject, &SSSMatType);
+  if (!op) return PyErr_NoMemory();
+  op->n = n; op->nnz = nnz; op->dev = NULL;
+  op->base[0] = op->base[1] = op->base[2] = op->base[3] = NULL;
+  op->val = PyMem_New(double, nnz > 0 ? nnz : 1);
+  op->diag = PyMem_New(double, n > 0 ? n : 1);
+  op->col = PyMem_New(int, nnz > 0 ? nnz : 1);
+  op->ind = PyMem_New(int, n + 1);
+  if (!op->val || !op->diag || !op->col || !op->ind) {
+    PyMem_Free(op->val); PyMem_Free(op->diag); PyMem_Free(op->col); PyMem_Free(op->ind);
+    PyObject_Del(op);
+    return PyErr_NoMemory();
+  }
+  return (PyObject *)op;
+}
+
+static psp_mat *sss_device(SSSMatObject *self)
+{
+  if (!self->dev) {
+    int st = psp_sss_create(self->n, self->nnz, self->ind, self->col, self->val, self->diag, &self->dev);
+    if (st != PSP_OK) { psp_raise(st); return NULL; }
+  }
+  return self->dev;
+}
+
+static void SSSMat_dealloc(SSSMatObject *self)
+{
+  if (self->dev) psp_mat_destroy(self->dev);
+  if (self->base[0]) { for (int k = 0; k < 4; k++) Py_XDECREF(self->base[k]); }
+  else { PyMem_Free(self->val); PyMem_Free(self->diag); PyMem_Free(self->col); PyMem_Free(self->ind); }
+  PyObject_Del(self);
+}
+
+/* matvec and matvec_transp are the same function (sss_mat.c:106-110) */
+static PyObject *SSSMat_matvec(SSSMatObject *self, PyObject *args)
+{
+  PyArrayObject *x, *y;
+  if (parse_vec_pair(args, &x, &y, self->n, self->n, 0)) return NULL;
+  psp_mat *d = sss_device(self);
+  return d ? device_matvec(d, 0, x, y) : NULL;
+}
+
+static PyObject *SSSMat_get_shape(SSSMatObject *self, void *c) { return Py_BuildValue("(i,i)", self->n, self->n); }
+/* nnz reports lower triangle + diagonal (sss_mat.c:155) */
+static PyObject *SSSMat_get_nnz(SSSMatObject *self, void *c) { return PyLong_FromLong(self->nnz + self->n); }
+static PyObject *SSSMat_get_dev(SSSMatObject *self, void *c)
+{
+  psp_mat *d = sss_device(self);
+  return d ? PyCapsule_New(d, PSP_MAT_CAPSULE, mat_capsule_noop) : NULL;
+}
+static PyObject *SSSMat_arrays(SSSMatObject *self, PyObject *noargs)
+{
+  return Py_BuildValue("(NNNN)", wrap_f64(self->val, self->nnz, (PyObject *)self),
+                       wrap_f64(self->diag, self->n, (PyObject *)self),
+                       wrap_i32(self->col, self->nnz, (PyObject *)self),
+                       wrap_i32(self->ind, self->n + 1, (PyObject *)self));
+}
+static PyObject *SSSMat_diagonal(SSSMatObject *self, PyObject *noargs)
+{
+  npy_intp n = self->n;
+  PyObject *a = PyArray_SimpleNew(1, &n, NPY_DOUBLE);
+  if (a && n) memcpy(PyArray_DATA((PyArrayObject *)a), self->diag, sizeof(double) * (size_t)n);
+  return a;
+}
+
+static double sss_get(SSSMatObject *self, int i, int j)
+{
+  if (i == j) return self->diag[i];
+  if (i < j) { int t = i; i = j; j = t; }
+  for (int k = self->ind[i]; k < self->ind[i + 1]; k++)
+    if (self->col[k] == j) return self->val[k];
+  return 0.0;
+}
+
+/* a[i,j] for integer pairs.  (In the reference snapshot this lookup always
+ * raises because LLMat_parse_index is a stub, ll_mat.c:3798-3806; the intended
+ * behaviour, sss_mat.c:14-28, is implemented here.) */
+static PyObject *pair_subscript(PyObject *idx, int n0, int n1, long *i, long *j)
+{
+  if (!PyTuple_Check(idx) || PyTuple_GET_SIZE(idx) != 2) {
+    PyErr_SetString(PyExc_IndexError, "index must be a pair (i, j)");
+    return NULL;
+  }
+  *i = PyLong_AsLong(PyTuple_GET_ITEM(idx, 0));
+  *j = PyLong_AsLong(PyTuple_GET_ITEM(idx, 1));
+  if (PyErr_Occurred()) { PyErr_Clear(); PyErr_SetString(PyExc_IndexError, "indices must be integers"); return NULL; }
+  if (*i < 0) *i += n0;
+  if (*j < 0) *j += n1;
+  if (*i < 0 || *j < 0 || *i >= n0 || *j >= n1) { PyErr_SetString(PyExc_IndexError, "indices out of range"); return NULL; }
+  return idx;
+}
+static PyObject *SSSMat_subscript(SSSMatObject *self, PyObject *idx)
+{
+  long i, j;
+  if (!pair_subscript(idx, self->n, self->n, &i, &j)) return NULL;
+  return PyFloat_FromDouble(sss_get(self, (int)i, (int)j));
+}
+static PyObject *CSRMat_subscript(CSRMatObject *self, PyObject *idx)
+{
+  long i, j;
+  if (!pair_subscript(idx, self->dim[0], self->dim[1], &i, &j)) return NULL;
+  return PyFloat_FromDouble(csr_get(self, (int)i, (int)j));
+}
+static PyMappingMethods SSSMat_as_mapping = {0, (binaryfunc)SSSMat_subscript, 0};
+static PyMappingMethods CSRMat_as_mapping = {0, (binaryfunc)CSRMat_subscript, 0};
+
+static PyMethodDef SSSMat_methods[] = {
+  {"matvec", (PyCFunction)SSSMat_matvec, METH_VARARGS, "a.matvec(x, y)\n\ncompute the sparse matrix-vector product y := a * x."},
+  {"matvec_transp", (PyCFunction)SSSMat_matvec, METH_VARARGS, "a.matvec_transp(x, y)\n\nsame as matvec (a is symmetric)."},
+  {"arrays", (PyCFunction)SSSMat_arrays, METH_NOARGS, "(val, diag, col, ind) read-only views of the SSS storage"},
+  {"diagonal", (PyCFunction)SSSMat_diagonal, METH_NOARGS, "dense copy of the diagonal"},
+  {NULL, NULL}
+};
+static PyGetSetDef SSSMat_getset[] = {
+  {"shape", (getter)SSSMat_get_shape, NULL, NULL, NULL},
+  {"nnz", (getter)SSSMat_get_nnz, NULL, NULL, NULL},
+  {"_psp_mat", (getter)SSSMat_get_dev, NULL, "device handle (PyCapsule)", NULL},
+  {NULL}
+};
+
+/* ========================================================================= */
+/* ll_mat                                                                      */
+/* ========================================================================= */
+static PyObject *SpMatrix_NewLLMatObject(int dim[], int sym, int sizeHint, int storeZeros)
+{
+  if (dim[0] < 0 || dim[1] < 0) { PyErr_SetString(PyExc_ValueError, "matrix dimension must be non-negative"); return NULL; }
+  if (sizeHint < 1) sizeHint = 1;
+  LLMatObject *op = PyObject_New(LLMatObject, &LLMatType);
+  if (!op) return PyErr_NoMemory();
+  op->dim[0] = dim[0]; op->dim[1] = dim[1]; op->issym = sym; op->storeZeros = storeZeros; op->nnz = 0;
+  op->version = 1; op->dev_version = 0; op->dev = NULL;
+  op->rows = (LLRow *)calloc((size_t)(dim[0] > 0 ? dim[0] : 1), sizeof(LLRow));
+  if (!op->rows) { PyObject_Del(op); return PyErr_NoMemory(); }
+  return (PyObject *)op;
+}
+
+static void LLMat_dealloc(LLMatObject *self)
+{
+  if (self->dev) psp_mat_destroy(self->dev);
+  for (int i = 0; i < self->dim[0]; i++) { free(self->rows[i].col); free(self->rows[i].val); }
+  free(self->rows);
+  PyObject_Del(self);
+}
+
+/* position of column j in row r (lower bound) */
+static int row_find(const LLRow *r, int j)
+{
+  int lo = 0, hi = r->len;
+  while (lo < hi) { int mid = (lo + hi) >> 1; if (r->col[mid] < j) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+
+static int row_insert(LLRow *r, int pos, int j, double x)
+{
+  if (r->len == r->cap) {
+    int ncap = r->cap ? r->cap * 2 : 8;
+    int *nc = (int *)realloc(r->col, sizeof(int) * (size_t)ncap);
+    if (!nc) return -1;
+    r->col = nc;
+    double *nv = (double *)realloc(r->val, sizeof(double) * (size_t)ncap);
+    if (!nv) return -1;
+    r->val = nv;
+    r->cap = ncap;
+  }
+  memmove(r->col + pos + 1, r->col + pos, sizeof(int) * (size_t)(r->len - pos));
+  memmove(r->val + pos + 1, r->val + pos, sizeof(double) * (size_t)(r->len - pos));
+  r->col[pos] = j; r->val[pos] = x; r->len++;
+  return 0;
+}
+
+static void row_remove(LLRow *r, int pos)
+{
+  memmove(r->col + pos, r->col + pos + 1, sizeof(int) * (size_t)(r->len - pos - 1));
+  memmove(r->val + pos, r->val + pos + 1, sizeof(double) * (size_t)(r->len - pos - 1));
+  r->len--;
+}
+
+/* a[i,j]   (SpMatrix_LLMatGetItem, ll_mat.c:210-245) */
+static double SpMatrix_LLMatGetItem(LLMatObject *a, int i, int j)
+{
+  if (i < 0 || i >= a->dim[0] || j < 0 || j >= a->dim[1]) {
+    PyErr_SetString(PyExc_IndexError, "indices out of range");
+    return 0.0;
+  }
+  if (a->issym && i < j) { int t = i; i = j; j = t; }
+  const LLRow *r = &a->rows[i];
+  int pos = row_find(r, j);
+  return (pos < r->len && r->col[pos] == j) ? r->val[pos] : 0.0;
+}
+
+/* a[i,j] = x   (SpMatrix_LLMatSetItem, ll_mat.c:251-352) */
+static int SpMatrix_LLMatSetItem(LLMatObject *a, int i, int j, double x)
+{
+  if (a->issym && i < j) {
+    PyErr_SetString(PyExc_IndexError, "write operation to upper triangle of symmetric matrix");
+    return -1;
+  }
+  if (i < 0 || i >= a->dim[0] || j < 0 || j >= a->dim[1]) {
+    PyErr_SetString(PyExc_IndexError, "indices out of range");
+    return -1;
+  }
+  LLRow *r = &a->rows[i];
+  int pos = row_find(r, j);
+  int found = (pos < r->len && r->col[pos] == j);
+  if (x != 0.0 || a->storeZeros == 1) {
+    if (found) r->val[pos] = x;
+    else {
+      if (row_insert(r, pos, j, x)) { PyErr_NoMemory(); return -1; }
+      a->nnz++;
+    }
+  } else if (found) {
+    row_remove(r, pos);
+    a->nnz--;
+  }
+  a->version++;
+  return 0;
+}
+
+/* a[i,j] += x   (SpMatrix_LLMatUpdateItemAdd, ll_mat.c:358-457) */
+static int SpMatrix_LLMatUpdateItemAdd(LLMatObject *a, int i, int j, double x)
+{
+  if (a->issym && i < j) {
+    PyErr_SetString(PyExc_IndexError, "write operation to upper triangle of symmetric matrix");
+    return -1;
+  }
+  if (i < 0 || i >= a->dim[0] || j < 0 || j >= a->dim[1]) {
+    PyErr_SetString(PyExc_IndexError, "indices out of range");
+    return -1;
+  }
+  if (a->storeZeros == 0 && x == 0.0) return 0;
+  LLRow *r = &a->rows[i];
+  int pos = row_find(r, j);
+  if (pos < r->len && r->col[pos] == j) {
+    x += r->val[pos];
+    if (a->storeZeros == 0 && x == 0.0) { row_remove(r, pos); a->nnz--; }
+    else r->val[pos] = x;
+  } else {
+    if (row_insert(r, pos, j, x)) { PyErr_NoMemory(); return -1; }
+    a->nnz++;
+  }
+  a->version++;
+  return 0;
+}
+
+/* column-linked index of the reference (ll_mat.c:135-201): tied to its linked
+ * list layout, which this container does not have. */
+struct llColIndex;
+static int SpMatrix_LLMatBuildColIndex(struct llColIndex **idx, LLMatObject *self, int includeDiagonal)
+{
+  (void)idx; (void)self; (void)includeDiagonal;
+  PyErr_SetString(PyExc_NotImplementedError, "llColIndex is not available in pysparse_b200 (row-array ll_mat)");
+  return 1;
+}
+static void SpMatrix_LLMatDestroyColIndex(struct llColIndex **idx) { (void)idx; }
+
+/* ---- conversions --------------------------------------------------------- */
+
+/* A.to_csr()   (LLMat_to_csr, ll_mat.c:1577-1648): general matrices are copied
+ * row by row; symmetric ones are expanded: row i = its stored (lower + diag)
+ * entries, then the column-i entries of the rows below it, ascending. */
+static PyObject *LLMat_to_csr(LLMatObject *self, PyObject *noargs)
+{
+  const int m = self->dim[0];
+  if (!self->issym) {
+    CSRMatObject *op = (CSRMatObject *)newCSRMatObject(self->dim, self->nnz);
+    if (!op) return NULL;
+    int r = 0;
+    op->ind[0] = 0;
+    for (int i = 0; i < m; i++) {
+      const LLRow *row = &self->rows[i];
+      memcpy(op->col + r, row->col, sizeof(int) * (size_t)row->len);
+      memcpy(op->val + r, row->val, sizeof(double) * (size_t)row->len);
+      r += row->len;
+      op->ind[i + 1] = r;
+    }
+    return (PyObject *)op;
+  }
+  long nlo = 0, ndiag = 0;
+  int *cnt = (int *)calloc((size_t)m + 1, sizeof(int));
+  if (!cnt) return PyErr_NoMemory();
+  for (int i = 0; i < m; i++) {
+    const LLRow *row = &self->rows[i];
+    cnt[i] += row->len;
+    for (int k = 0; k < row->len; k++) {
+      if (row->col[k] < i) { nlo++; cnt[row->col[k]]++; }
+      else ndiag++;
+    }
+  }
+  if (2 * nlo + ndiag >= 2147483647L) { free(cnt); PyErr_SetString(PyExc_OverflowError, "too many non-zeros for int32 CSR"); return NULL; }
+  CSRMatObject *op = (CSRMatObject *)newCSRMatObject(self->dim, (int)(2 * nlo + ndiag));
+  if (!op) { free(cnt); return NULL; }
+  op->ind[0] = 0;
+  for (int i = 0; i < m; i++) op->ind[i + 1] = op->ind[i] + cnt[i];
+  /* cnt becomes the fill cursor of the "upper" part of each row */
+  for (int i = 0; i < m; i++) {
+    const LLRow *row = &self->rows[i];
+    int p = op->ind[i];
+    memcpy(op->col + p, row->col, sizeof(int) * (size_t)row->len);
+    memcpy(op->val + p, row->val, sizeof(double) * (size_t)row->len);
+    cnt[i] = p + row->len;
+  }
+  for (int i = 0; i < m; i++) {
+    const LLRow *row = &self->rows[i];
+    for (int k = 0; k < row->len; k++) {
+      int j = row->col[k];
+      if (j < i) { op->col[cnt[j]] = i; op->val[cnt[j]] = row->val[k]; cnt[j]++; }
+    }
+  }
+  free(cnt);
+  return (PyObject *)op;
+}
+
+/* A.to_sss()   (LLMat_to_sss, ll_mat.c:1654-1708): strict lower triangle +
+ * diagonal; entries above the diagonal are silently dropped. */
+static PyObject *LLMat_to_sss(LLMatObject *self, PyObject *noargs)
+{
+  const int n = self->dim[0];
+  if (n != self->dim[1]) { PyErr_SetString(PyExc_ValueError, "Matrix must be square"); return NULL; }
+  long nnz = 0;
+  for (int i = 0; i < n; i++) nnz += row_find(&self->rows[i], i);
+  SSSMatObject *op = (SSSMatObject *)newSSSMatObject(n, (int)nnz);
+  if (!op) return NULL;
+  int r = 0;
+  op->ind[0] = 0;
+  for (int i = 0; i < n; i++) {
+    const LLRow *row = &self->rows[i];
+    int nl = row_find(row, i);
+    memcpy(op->col + r, row->col, sizeof(int) * (size_t)nl);
+    memcpy(op->val + r, row->val, sizeof(double) * (size_t)nl);
+    r += nl;
+    op->diag[i] = (nl < row->len && row->col[nl] == i) ? row->val[nl] : 0.0;
+    op->ind[i + 1] = r;
+  }
+  return (PyObject *)op;
+}
+
+/* device copy of an ll_mat: CSR for general, SSS for symmetric matrices
+ * (the same accumulation orders as ll_matvec_kernel / ll_matvec_kernel_sym,
+ * ll_mat.c:1262-1316); rebuilt when the matrix has been modified. */
+static psp_mat *ll_device(LLMatObject *self)
+{
+  if (self->dev && self->dev_version == self->version) return self->dev;
+  if (self->dev) { psp_mat_destroy(self->dev); self->dev = NULL; }
+  int st;
+  if (self->issym) {
+    SSSMatObject *s = (SSSMatObject *)LLMat_to_sss(self, NULL);
+    if (!s) return NULL;
+    st = psp_sss_create(s->n, s->nnz, s->ind, s->col, s->val, s->diag, &self->dev);
+    Py_DECREF(s);
+  } else {
+    CSRMatObject *c = (CSRMatObject *)LLMat_to_csr(self, NULL);
+    if (!c) return NULL;
+    st = psp_csr_create(c->dim[0], c->dim[1], c->nnz, c->ind, c->col, c->val, &self->dev);
+    Py_DECREF(c);
+  }
+  if (st != PSP_OK) { psp_raise(st); return NULL; }
+  self->dev_version = self->version;
+  return self->dev;
+}
+
+static PyObject *LLMat_matvec(LLMatObject *self, PyObject *args)
+{
+  PyArrayObject *x, *y;
+  if (parse_vec_pair(args, &x, &y, self->dim[1], self->dim[0], 0)) return NULL;
+  psp_mat *d = ll_device(self);
+  return d ? device_matvec(d, 0, x, y) : NULL;
+}
+static PyObject *LLMat_matvec_transp(LLMatObject *self, PyObject *args)
+{
+  PyArrayObject *x, *y;
+  if (parse_vec_pair(args, &x, &y, self->dim[0], self->dim[1], 0)) return NULL;
+  psp_mat *d = ll_device(self);
+  return d ? device_matvec(d, self->issym ? 0 : 1, x, y) : NULL;
+}
+
+/* ---- bulk element access -------------------------------------------------- */
+static int as_index_array(PyObject *o, PyArrayObject **out)
+{
+  *out = (PyArrayObject *)PyArray_FROM_OTF(o, NPY_LONG, NPY_ARRAY_IN_ARRAY);
+  if (!*out) return -1;
+  if (PyArray_NDIM(*out) > 1) { Py_DECREF(*out); *out = NULL; PyErr_SetString(PyExc_ValueError, "index arrays must be 1-dimensional"); return -1; }
+  return 0;
+}
+
+/* a.put(b, id1=None, id2=None) / a.update_add_at(b, id1, id2)   (ll_mat.c:1847, :2498) */
+static PyObject *put_like(LLMatObject *self, PyObject *args, int add)
+{
+  PyObject *bIn, *id1in = NULL, *id2in = NULL;
+  if (!PyArg_ParseTuple(args, add ? "OOO" : "O|OO", &bIn, &id1in, &id2in)) return NULL;
+  PyArrayObject *b = (PyArrayObject *)PyArray_FROM_OTF(bIn, NPY_DOUBLE, NPY_ARRAY_IN_ARRAY);
+  if (!b) return NULL;
+  PyArrayObject *i1 = NULL, *i2 = NULL;
+  PyObject *ret = NULL;
+  int b_scalar = (PyArray_NDIM(b) == 0);
+  if (id1in && id1in != Py_None && as_index_array(id1in, &i1)) goto done;
+  if (id2in && id2in != Py_None && as_index_array(id2in, &i2)) goto done;
+  long len;
+  if (i1) len = (long)PyArray_SIZE(i1);
+  else if (i2) len = (long)PyArray_SIZE(i2);
+  else if (!b_scalar) len = (long)PyArray_SIZE(b);
+  else { PyErr_SetString(PyExc_ValueError, "put: no index arrays and scalar value"); goto done; }
+  if ((!b_scalar && PyArray_SIZE(b) != len) || (i1 && PyArray_SIZE(i1) != len) || (i2 && PyArray_SIZE(i2) != len)) {
+    PyErr_SetString(PyExc_IndexError, "Not as many row indices as values");
+    goto done;
+  }
+  const double *bv = (const double *)PyArray_DATA(b);
+  const long *p1 = i1 ? (const long *)PyArray_DATA(i1) : NULL;
+  const long *p2 = i2 ? (const long *)PyArray_DATA(i2) : NULL;
+  for (long k = 0; k < len; k++) {
+    long r = p1 ? p1[k] : k;
+    long c = p2 ? p2[k] : r;
+    double v = b_scalar ? bv[0] : bv[k];
+    if (r < 0) r += self->dim[0];
+    if (c < 0) c += self->dim[1];
+    int rc = add ? SpMatrix_LLMatUpdateItemAdd(self, (int)r, (int)c, v) : SpMatrix_LLMatSetItem(self, (int)r, (int)c, v);
+    if (rc) goto done;
+  }
+  Py_INCREF(Py_None);
+  ret = Py_None;
+done:
+  Py_XDECREF(b); Py_XDECREF(i1); Py_XDECREF(i2);
+  return ret;
+}
+static PyObject *LLMat_put(LLMatObject *self, PyObject *args) { return put_like(self, args, 0); }
+static PyObject *LLMat_update_add_at(LLMatObject *self, PyObject *args) { return put_like(self, args, 1); }
+
+/* val, irow, jcol = a.find()   (LLMat_Find, ll_mat.c:2999-3035) */
+static PyObject *LLMat_find(LLMatObject *self, PyObject *noargs)
+{
+  npy_intp n = self->nnz;
+  PyObject *ar = PyArray_SimpleNew(1, &n, NPY_INT), *ac = PyArray_SimpleNew(1, &n, NPY_INT), *av = PyArray_SimpleNew(1, &n, NPY_DOUBLE);
+  if (!ar || !ac || !av) { Py_XDECREF(ar); Py_XDECREF(ac); Py_XDECREF(av); return NULL; }
+  int *pi = (int *)PyArray_DATA((PyArrayObject *)ar), *pj = (int *)PyArray_DATA((PyArrayObject *)ac);
+  double *pv = (double *)PyArray_DATA((PyArrayObject *)av);
+  long e = 0;
+  for (int i = 0; i < self->dim[0]; i++) {
+    const LLRow *r = &self->rows[i];
+    for (int k = 0; k < r->len; k++, e++) { pi[e] = i; pj[e] = r->col[k]; pv[e] = r->val[k]; }
+  }
+  return Py_BuildValue("NNN", av, ar, ac);
+}
+
+/* a.take(b, id1=None, id2=None): b[k] = a[id1[k], id2[k]]   (ll_mat.c LLMat_take) */
+static PyObject *LLMat_take(LLMatObject *self, PyObject *args)
+{
+  PyObject *bIn, *id1in = NULL, *id2in = NULL;
+  if (!PyArg_ParseTuple(args, "O!|OO", &PyArray_Type, &bIn, &id1in, &id2in)) return NULL;
+  PyArrayObject *b = (PyArrayObject *)bIn, *i1 = NULL, *i2 = NULL;
+  if (PyArray_TYPE(b) != NPY_DOUBLE || PyArray_NDIM(b) != 1 || !PyArray_IS_C_CONTIGUOUS(b)) {
+    PyErr_SetString(PyExc_ValueError, "b must be a contiguous 1-dimensional double array");
+    return NULL;
+  }
+  PyObject *ret = NULL;
+  if (id1in && id1in != Py_None && as_index_array(id1in, &i1)) goto done;
+  if (id2in && id2in != Py_None && as_index_array(id2in, &i2)) goto done;
+  long len = (long)PyArray_SIZE(b);
+  if ((i1 && PyArray_SIZE(i1) != len) || (i2 && PyArray_SIZE(i2) != len)) { PyErr_SetString(PyExc_IndexError, "Not as many indices as values"); goto done; }
+  double *bv = (double *)PyArray_DATA(b);
+  const long *p1 = i1 ? (const long *)PyArray_DATA(i1) : NULL, *p2 = i2 ? (const long *)PyArray_DATA(i2) : NULL;
+  for (long k = 0; k < len; k++) {
+    long r = p1 ? p1[k] : k, c = p2 ? p2[k] : r;
+    if (r < 0) r += self->dim[0];
+    if (c < 0) c += self->dim[1];
+    bv[k] = SpMatrix_LLMatGetItem(self, (int)r, (int)c);
+    if (PyErr_Occurred()) goto done;
+  }
+  Py_INCREF(Py_None);
+  ret = Py_None;
+done:
+  Py_XDECREF(i1); Py_XDECREF(i2);
+  return ret;
+}
+
+static PyObject *LLMat_keys_values_items(LLMatObject *self, int what)
+{
+  PyObject *list = PyList_New(self->nnz);
+  if (!list) return NULL;
+  Py_ssize_t e = 0;
+  for (int i = 0; i < self->dim[0]; i++) {
+    const LLRow *r = &self->rows[i];
+    for (int k = 0; k < r->len; k++, e++) {
+      PyObject *o;
+      if (what == 0) o = Py_BuildValue("(ii)", i, r->col[k]);
+      else if (what == 1) o = PyFloat_FromDouble(r->val[k]);
+      else o = Py_BuildValue("((ii)d)", i, r->col[k], r->val[k]);
+      if (!o) { Py_DECREF(list); return NULL; }
+      PyList_SET_ITEM(list, e, o);
+    }
+  }
+  return list;
+}
+static PyObject *LLMat_keys(LLMatObject *self, PyObject *n) { return LLMat_keys_values_items(self, 0); }
+static PyObject *LLMat_values(LLMatObject *self, PyObject *n) { return LLMat_keys_values_items(self, 1); }
+static PyObject *LLMat_items(LLMatObject *self, PyObject *n) { return LLMat_keys_values_items(self, 2); }
+
+static PyObject *LLMat_copy(LLMatObject *self, PyObject *noargs)
+{
+  LLMatObject *c = (LLMatObject *)SpMatrix_NewLLMatObject(self->dim, self->issym, self->nnz, self->storeZeros);
+  if (!c) return NULL;
+  for (int i = 0; i < self->dim[0]; i++) {
+    const LLRow *s = &self->rows[i];
+    LLRow *d = &c->rows[i];
+    if (!s->len) continue;
+    d->col = (int *)malloc(sizeof(int) * (size_t)s->len);
+    d->val = (double *)malloc(sizeof(double) * (size_t)s->len);
+    if (!d->col || !d->val) { Py_DECREF(c); return PyErr_NoMemory(); }
+    memcpy(d->col, s->col, sizeof(int) * (size_t)s->len);
+    memcpy(d->val, s->val, sizeof(double) * (size_t)s->len);
+    d->len = d->cap = s->len;
+  }
+  c->nnz = self->nnz;
+  return (PyObject *)c;
+}
+
+static PyObject *LLMat_scale(LLMatObject *self, PyObject *args)
+{
+  double f;
+  if (!PyArg_ParseTuple(args, "d", &f)) return NULL;
+  for (int i = 0; i < self->dim[0]; i++) for (int k = 0; k < self->rows[i].len; k++) self->rows[i].val[k] *= f;
+  self->version++;
+  Py_RETURN_NONE;
+}
+
+/* a.shift(sigma, b): a += sigma * b   (LLMat_shift, ll_mat.c) */
+static PyObject *LLMat_shift(LLMatObject *self, PyObject *args)
+{
+  double sigma;
+  LLMatObject *b;
+  if (!PyArg_ParseTuple(args, "dO!", &sigma, &LLMatType, &b)) return NULL;
+  if (self->dim[0] != b->dim[0] || self->dim[1] != b->dim[1]) { PyErr_SetString(PyExc_ValueError, "matrix shapes do not match"); return NULL; }
+  if (self->issym && !b->issym) { PyErr_SetString(PyExc_ValueError, "cannot shift symmetric matrix by non-symmetric matrix"); return NULL; }
+  for (int i = 0; i < b->dim[0]; i++) {
+    const LLRow *r = &b->rows[i];
+    for (int k = 0; k < r->len; k++) {
+      int j = r->col[k];
+      if (SpMatrix_LLMatUpdateItemAdd(self, i, j, sigma * r->val[k])) return NULL;
+      if (b->issym && !self->issym && i != j && SpMatrix_LLMatUpdateItemAdd(self, j, i, sigma * r->val[k])) return NULL;
+    }
+  }
+  Py_RETURN_NONE;
+}
+
+/* a.norm(p): p in '1', 'inf', 'fro'   (LLMat_norm, ll_mat.c) */
+static PyObject *LLMat_norm(LLMatObject *self, PyObject *args)
+{
+  const char *p;
+  if (!PyArg_ParseTuple(args, "s", &p)) return NULL;
+  const int m = self->dim[0], n = self->dim[1];
+  double res = 0.0;
+  if (!strcmp(p, "fro")) {
+    for (int i = 0; i < m; i++) {
+      const LLRow *r = &self->rows[i];
+      for (int k = 0; k < r->len; k++) {
+        double v = r->val[k] * r->val[k];
+        res += (self->issym && r->col[k] != i) ? 2.0 * v : v;
+      }
+    }
+    return PyFloat_FromDouble(sqrt(res));
+  }
+  int by_col = !strcmp(p, "1");
+  if (!by_col && strcmp(p, "inf")) { PyErr_SetString(PyExc_ValueError, "unknown norm"); return NULL; }
+  int len = by_col ? n : m;
+  if (self->issym) len = m;
+  double *s = (double *)calloc((size_t)(len > 0 ? len : 1), sizeof(double));
+  if (!s) return PyErr_NoMemory();
+  for (int i = 0; i < m; i++) {
+    const LLRow *r = &self->rows[i];
+    for (int k = 0; k < r->len; k++) {
+      double v = fabs(r->val[k]);
+      int j = r->col[k];
+      if (self->issym) { s[i] += v; if (i != j) s[j] += v; }
+      else s[by_col ? j : i] += v;
+    }
+  }
+  for (int i = 0; i < len; i++) if (s[i] > res) res = s[i];
+  free(s);
+  return PyFloat_FromDouble(res);
+}
+
+static PyObject *LLMat_generalize(LLMatObject *self, PyObject *noargs)
+{
+  if (self->issym) {
+    self->issym = 0;
+    for (int i = 0; i < self->dim[0]; i++) {
+      int nl = row_find(&self->rows[i], i);
+      for (int k = 0; k < nl; k++)
+        if (SpMatrix_LLMatSetItem(self, self->rows[i].col[k], i, self->rows[i].val[k])) return NULL;
+    }
+  }
+  Py_RETURN_NONE;
+}
+
+static PyObject *LLMat_compress(LLMatObject *self, PyObject *noargs)
+{
+  long freed = 0;
+  for (int i = 0; i < self->dim[0]; i++) {
+    LLRow *r = &self->rows[i];
+    if (r->cap > r->len) {
+      freed += r->cap - r->len;
+      if (r->len == 0) { free(r->col); free(r->val); r->col = NULL; r->val = NULL; r->cap = 0; }
+      else {
+        r->col = (int *)realloc(r->col, sizeof(int) * (size_t)r->len);
+        r->val = (double *)realloc(r->val, sizeof(double) * (size_t)r->len);
+        r->cap = r->len;
+      }
+    }
+  }
+  return PyLong_FromLong(freed);
+}
+
+/* a.export_mtx(fileName, precision=16)   (MatrixMarket coordinate real) */
+static PyObject *LLMat_export_mtx(LLMatObject *self, PyObject *args)
+{
+  const char *fname; int prec = 16;
+  if (!PyArg_ParseTuple(args, "s|i", &fname, &prec)) return NULL;
+  FILE *f = fopen(fname, "w");
+  if (!f) return PyErr_SetFromErrnoWithFilename(PyExc_IOError, fname);
+  fprintf(f, "%%%%MatrixMarket matrix coordinate real %s\n", self->issym ? "symmetric" : "general");
+  fprintf(f, "%d %d %d\n", self->dim[0], self->dim[1], self->nnz);
+  for (int i = 0; i < self->dim[0]; i++)
+    for (int k = 0; k < self->rows[i].len; k++)
+      fprintf(f, "%d %d %.*e\n", i + 1, self->rows[i].col[k] + 1, prec - 1, self->rows[i].val[k]);
+  fclose(f);
+  Py_RETURN_NONE;
+}
+
+static PyObject *LLMat_get_dev(LLMatObject *self, void *c)
+{
+  psp_mat *d = ll_device(self);
+  return d ? PyCapsule_New(d, PSP_MAT_CAPSULE, mat_capsule_noop) : NULL;
+}
+static PyObject *LLMat_get_shape(LLMatObject *self, void *c) { return Py_BuildValue("(i,i)", self->dim[0], self->dim[1]); }
+static PyObject *LLMat_get_nnz(LLMatObject *self, void *c) { return PyLong_FromLong(self->nnz); }
+static PyObject *LLMat_get_issym(LLMatObject *self, void *c) { return PyLong_FromLong(self->issym); }
+
+/* ---- subscripting: integer pairs and slices ------------------------------- */
+static int norm_index(PyObject *o, int dim, Py_ssize_t *start, Py_ssize_t *stop, Py_ssize_t *step, Py_ssize_t *len, int *is_int)
+{
+  if (PyLong_Check(o)) {
+    long v = PyLong_AsLong(o);
+    if (v == -1 && PyErr_Occurred()) return -1;
+    while (v < 0) v += dim;                      /* ll_mat.c:644-645 */
+    if (v >= dim) { PyErr_SetString(PyExc_IndexError, "Index out of bounds"); return -1; }
+    *start = v; *stop = v + 1; *step = 1; *len = 1; *is_int = 1;
+    return 0;
+  }
+  if (PySlice_Check(o)) {
+    if (PySlice_Unpack(o, start, stop, step) < 0) return -1;
+    *len = PySlice_AdjustIndices(dim, start, stop, *step);
+    *is_int = 0;
+    return 0;
+  }
+  PyErr_SetString(PyExc_IndexError, "Index must be an integer or a slice");
+  return -1;
+}
+
+static PyObject *LLMat_subscript(LLMatObject *self, PyObject *idx)
+{
+  if (!PyTuple_Check(idx) || PyTuple_GET_SIZE(idx) != 2) { PyErr_SetString(PyExc_IndexError, "Index must be a pair"); return NULL; }
+  Py_ssize_t s0, e0, st0, l0, s1, e1, st1, l1; int int0, int1;
+  if (norm_index(PyTuple_GET_ITEM(idx, 0), self->dim[0], &s0, &e0, &st0, &l0, &int0)) return NULL;
+  if (norm_index(PyTuple_GET_ITEM(idx, 1), self->dim[1], &s1, &e1, &st1, &l1, &int1)) return NULL;
+  if (int0 && int1) return PyFloat_FromDouble(SpMatrix_LLMatGetItem(self, (int)s0, (int)s1));
+  int dim[2] = {(int)l0, (int)l1};
+  LLMatObject *dst = (LLMatObject *)SpMatrix_NewLLMatObject(dim, 0, 16, self->storeZeros);
+  if (!dst) return NULL;
+  for (Py_ssize_t a = 0; a < l0; a++)
+    for (Py_ssize_t b = 0; b < l1; b++) {
+      double v = SpMatrix_LLMatGetItem(self, (int)(s0 + a * st0), (int)(s1 + b * st1));
+      if (v != 0.0 && SpMatrix_LLMatSetItem(dst, (int)a, (int)b, v)) { Py_DECREF(dst); return NULL; }
+    }
+  return (PyObject *)dst;
+}
+
+static int LLMat_ass_subscript(LLMatObject *self, PyObject *idx, PyObject *value)
+{
+  if (!value) { PyErr_SetString(PyExc_TypeError, "cannot delete matrix entries"); return -1; }
+  if (!PyTuple_Check(idx) || PyTuple_GET_SIZE(idx) != 2) { PyErr_SetString(PyExc_IndexError, "Index must be a pair"); return -1; }
+  Py_ssize_t s0, e0, st0, l0, s1, e1, st1, l1; int int0, int1;
+  if (norm_index(PyTuple_GET_ITEM(idx, 0), self->dim[0], &s0, &e0, &st0, &l0, &int0)) return -1;
+  if (norm_index(PyTuple_GET_ITEM(idx, 1), self->dim[1], &s1, &e1, &st1, &l1, &int1)) return -1;
+  if (PyObject_TypeCheck(value, &LLMatType)) {
+    LLMatObject *src = (LLMatObject *)value;
+    if (src->dim[0] != l0 || src->dim[1] != l1) { PyErr_SetString(PyExc_ValueError, "Matrix shapes are different"); return -1; }
+    /* clear the target block, then copy (symmetric targets only receive i >= j) */
+    for (Py_ssize_t a = 0; a < l0; a++)
+      for (Py_ssize_t b = 0; b < l1; b++) {
+        int i = (int)(s0 + a * st0), j = (int)(s1 + b * st1);
+        if (self->issym && i < j) continue;
+        double v = SpMatrix_LLMatGetItem(src, (int)a, (int)b);
+        if (SpMatrix_LLMatSetItem(self, i, j, v)) return -1;
+      }
+    return 0;
+  }
+  double v = PyFloat_AsDouble(value);
+  if (v == -1.0 && PyErr_Occurred()) { PyErr_Clear(); PyErr_SetString(PyExc_ValueError, "Value must be double"); return -1; }
+  for (Py_ssize_t a = 0; a < l0; a++)
+    for (Py_ssize_t b = 0; b < l1; b++)
+      if (SpMatrix_LLMatSetItem(self, (int)(s0 + a * st0), (int)(s1 + b * st1), v)) return -1;
+  return 0;
+}
+static PyMappingMethods LLMat_as_mapping = {0, (binaryfunc)LLMat_subscript, (objobjargproc)LLMat_ass_subscript};
+
+static PyMethodDef LLMat_methods[] = {
+  {"matvec", (PyCFunction)LLMat_matvec, METH_VARARGS, "A.matvec(x, y)\n\ncompute the sparse matrix-vector product y := A * x."},
+  {"matvec_transp", (PyCFunction)LLMat_matvec_transp, METH_VARARGS, "A.matvec_transp(x, y)\n\ncompute y := A^T * x."},
+  {"to_csr", (PyCFunction)LLMat_to_csr, METH_NOARGS, "A.to_csr()\n\nreturn a new CSRMatObject constructed from data of A"},
+  {"to_sss", (PyCFunction)LLMat_to_sss, METH_NOARGS, "a.to_sss()\n\nreturn a new SSSMatObject constructed from the lower triangle of a"},
+  {"generalize", (PyCFunction)LLMat_generalize, METH_NOARGS, "convert ll_mat object from symmetric to non-symmetric form (in-place)."},
+  {"compress", (PyCFunction)LLMat_compress, METH_NOARGS, "release unused storage; returns the number of freed slots"},
+  {"export_mtx", (PyCFunction)LLMat_export_mtx, METH_VARARGS, "A.export_mtx(fileName, precision=16)"},
+  {"copy", (PyCFunction)LLMat_copy, METH_NOARGS, "A.copy()"},
+  {"norm", (PyCFunction)LLMat_norm, METH_VARARGS, "A.norm(p), p in '1', 'inf', 'fro'"},
+  {"shift", (PyCFunction)LLMat_shift, METH_VARARGS, "A.shift(sigma, B): A += sigma * B"},
+  {"scale", (PyCFunction)LLMat_scale, METH_VARARGS, "A.scale(sigma)"},
+  {"keys", (PyCFunction)LLMat_keys, METH_NOARGS, "list of (i, j) of the stored entries"},
+  {"values", (PyCFunction)LLMat_values, METH_NOARGS, "list of the stored values"},
+  {"items", (PyCFunction)LLMat_items, METH_NOARGS, "list of ((i, j), value)"},
+  {"put", (PyCFunction)LLMat_put, METH_VARARGS, "a.put(b, id1, id2): a[id1[i], id2[i]] = b[i]"},
+  {"take", (PyCFunction)LLMat_take, METH_VARARGS, "a.take(b, id1, id2): b[i] = a[id1[i], id2[i]]"},
+  {"find", (PyCFunction)LLMat_find, METH_NOARGS, "(val, irow, jcol) = a.find()"},
+  {"update_add_at", (PyCFunction)LLMat_update_add_at, METH_VARARGS, "a.update_add_at(b, id1, id2): a[id1[i], id2[i]] += b[i]"},
+  {NULL, NULL}
+};
+static PyGetSetDef LLMat_getset[] = {
+  {"shape", (getter)LLMat_get_shape, NULL, NULL, NULL},
+  {"nnz", (getter)LLMat_get_nnz, NULL, NULL, NULL},
+  {"issym", (getter)LLMat_get_issym, NULL, NULL, NULL},
+  {"_psp_mat", (getter)LLMat_get_dev, NULL, "device handle (PyCapsule)", NULL},
+  {NULL}
+};
+
+/* ========================================================================= */
+/* C-API functions (spmatrixmodule.c:42-307)                                   */
+/* ========================================================================= */
+static int SpMatrix_GetShape(PyObject *op, int dim[])
+{
+  PyObject *sh = PyObject_GetAttrString(op, "shape");
+  if (!sh) return -1;
+  if (PySequence_Size(sh) != 2) { Py_DECREF(sh); PyErr_SetString(PyExc_ValueError, "invalid matrix shape"); return -1; }
+  for (int k = 0; k < 2; k++) {
+    PyObject *e = PySequence_GetItem(sh, k);
+    dim[k] = e ? (int)PyLong_AsLong(e) : -1;
+    Py_XDECREF(e);
+  }
+  Py_DECREF(sh);
+  if (PyErr_Occurred()) { PyErr_Clear(); PyErr_SetString(PyExc_ValueError, "invalid matrix shape"); return -1; }
+  return 0;
+}
+
+static int SpMatrix_GetOrder(PyObject *op, int *n)
+{
+  int dim[2];
+  if (SpMatrix_GetShape(op, dim) == -1) return -1;
+  if (dim[0] != dim[1]) { PyErr_SetString(PyExc_ValueError, "matrix is not square"); return -1; }
+  *n = dim[0];
+  return 0;
+}
+
+static double SpMatrix_GetItem(PyObject *op, int i, int j)
+{
+  if (Py_TYPE(op) == &SSSMatType) return sss_get((SSSMatObject *)op, i, j);
+  if (Py_TYPE(op) == &CSRMatType) return csr_get((CSRMatObject *)op, i, j);
+  if (Py_TYPE(op) == &LLMatType) return SpMatrix_LLMatGetItem((LLMatObject *)op, i, j);
+  PyObject *index = Py_BuildValue("(ii)", i, j);
+  PyObject *fo = index ? PyObject_GetItem(op, index) : NULL;
+  Py_XDECREF(index);
+  if (!fo) return 0.0;
+  double d = PyFloat_AsDouble(fo);
+  Py_DECREF(fo);
+  return d;
+}
+
+static psp_mat *native_handle(PyObject *m)
+{
+  if (Py_TYPE(m) == &CSRMatType) return csr_device((CSRMatObject *)m);
+  if (Py_TYPE(m) == &SSSMatType) return sss_device((SSSMatObject *)m);
+  if (Py_TYPE(m) == &LLMatType) return ll_device((LLMatObject *)m);
+  return NULL;
+}
+
+/* y = matrix * x on raw host buffers (slot 7).  Native matrices go to the GPU;
+ * any other object is called back through its Python `matvec` method exactly
+ * like the reference does (spmatrixmodule.c:169-201). */
+static int SpMatrix_Matvec(PyObject *matrix, int nx, double *x, int ny, double *y)
+{
+  if (Py_TYPE(matrix) == &CSRMatType || Py_TYPE(matrix) == &SSSMatType || Py_TYPE(matrix) == &LLMatType) {
+    psp_mat *d = native_handle(matrix);
+    if (!d) return -1;
+    int st = psp_matvec(d, 0, x, 1, y, 1);
+    if (st != PSP_OK) { psp_raise(st); return -1; }
+    return 0;
+  }
+  npy_intp dx = nx, dy = ny;
+  PyObject *xa = PyArray_SimpleNewFromData(1, &dx, NPY_DOUBLE, x);
+  PyObject *ya = xa ? PyArray_SimpleNewFromData(1, &dy, NPY_DOUBLE, y) : NULL;
+  PyObject *res = ya ? PyObject_CallMethod(matrix, "matvec", "OO", xa, ya) : NULL;
+  Py_XDECREF(xa); Py_XDECREF(ya);
+  if (!res) return -1;
+  Py_DECREF(res);
+  return 0;
+}
+
+/* y = prec(x) (slot 8): always the Python `precon` method (spmatrixmodule.c:215-248);
+ * the native preconditioner objects implement it on the GPU. */
+static int SpMatrix_Precon(PyObject *prec, int n, double *x, double *y)
+{
+  npy_intp d = n;
+  PyObject *xa = PyArray_SimpleNewFromData(1, &d, NPY_DOUBLE, x);
+  PyObject *ya = xa ? PyArray_SimpleNewFromData(1, &d, NPY_DOUBLE, y) : NULL;
+  PyObject *res = ya ? PyObject_CallMethod(prec, "precon", "OO", xa, ya) : NULL;
+  Py_XDECREF(xa); Py_XDECREF(ya);
+  if (!res) return -1;
+  Py_DECREF(res);
+  return 0;
+}
+
+static int SpMatrix_ParseVecOpArgs(PyObject *args, double **x_data, double **y_data, int n)
+{
+  PyArrayObject *x, *y;
+  if (parse_vec_pair(args, &x, &y, n, n, 1)) return -1;
+  *x_data = (double *)PyArray_DATA(x);
+  *y_data = (double *)PyArray_DATA(y);
+  return 0;
+}
+
+/* slot 15 (spmatrixmodule.c:266-307): call linsolver(A, b, x, tol, itmax[, K]) */
+static int ItSolvers_Solve(PyObject *linsolver, PyObject *A, int n, double *b, double *x, double tol, int itmax,
+                           PyObject *K, int *info, int *iter, double *relres)
+{
+  npy_intp d = n;
+  PyObject *ba = PyArray_SimpleNewFromData(1, &d, NPY_DOUBLE, b);
+  PyObject *xa = ba ? PyArray_SimpleNewFromData(1, &d, NPY_DOUBLE, x) : NULL;
+  PyObject *res = NULL;
+  if (xa) res = K ? PyObject_CallFunction(linsolver, "OOOdiO", A, ba, xa, tol, itmax, K)
+                  : PyObject_CallFunction(linsolver, "OOOdi", A, ba, xa, tol, itmax);
+  Py_XDECREF(ba); Py_XDECREF(xa);
+  if (!res) return -1;
+  int ok = PyArg_ParseTuple(res, "iid", info, iter, relres);
+  Py_DECREF(res);
+  return ok ? 0 : -1;
+}
+
+/* ========================================================================= */
+/* module functions                                                            */
+/* ========================================================================= */
+static PyObject *LLMat_zeros(PyObject *self, PyObject *args)
+{
+  int dim[2], sizeHint = 1000, storeZeros = 0;
+  if (!PyArg_ParseTuple(args, "ii|ii", dim, dim + 1, &sizeHint, &storeZeros)) return NULL;
+  return SpMatrix_NewLLMatObject(dim, 0, sizeHint, storeZeros);
+}
+static PyObject *LLMat_sym_zeros(PyObject *self, PyObject *args)
+{
+  int dim[2], n, sizeHint = 1000, storeZeros = 0;
+  if (!PyArg_ParseTuple(args, "i|ii", &n, &sizeHint, &storeZeros)) return NULL;
+  dim[0] = dim[1] = n;
+  return SpMatrix_NewLLMatObject(dim, 1, sizeHint, storeZeros);
+}
+
+/* ll_mat_from_mtx(fileName)   (ll_mat.c:3390-3456): MatrixMarket coordinate real */
+static PyObject *LLMat_from_mtx(PyObject *self, PyObject *args)
+{
+  const char *fname;
+  if (!PyArg_ParseTuple(args, "s", &fname)) return NULL;
+  FILE *f = fopen(fname, "r");
+  if (!f) return PyErr_SetFromErrnoWithFilename(PyExc_IOError, fname);
+  char line[1024], obj[64], fmt[64], field[64], symm[64];
+  if (!fgets(line, sizeof line, f) || sscanf(line, "%%%%MatrixMarket %63s %63s %63s %63s", obj, fmt, field, symm) != 4 ||
+      strcmp(obj, "matrix") || strcmp(fmt, "coordinate")) {
+    fclose(f);
+    PyErr_SetString(PyExc_IOError, "error reading MatrixMarket header");
+    return NULL;
+  }
+  if (strcmp(field, "real") && strcmp(field, "integer")) { fclose(f); PyErr_SetString(PyExc_TypeError, "Matrix type not supported"); return NULL; }
+  int sym = !strcmp(symm, "symmetric");
+  do { if (!fgets(line, sizeof line, f)) { fclose(f); PyErr_SetString(PyExc_IOError, "error reading MatrixMarket file"); return NULL; } } while (line[0] == '%');
+  int dim[2]; long nz;
+  if (sscanf(line, "%d %d %ld", dim, dim + 1, &nz) != 3) { fclose(f); PyErr_SetString(PyExc_IOError, "error reading MatrixMarket size line"); return NULL; }
+  LLMatObject *A = (LLMatObject *)SpMatrix_NewLLMatObject(dim, sym, (int)nz, 0);
+  if (!A) { fclose(f); return NULL; }
+  for (long k = 0; k < nz; k++) {
+    int i, j; double v;
+    if (fscanf(f, "%d %d %lg", &i, &j, &v) != 3) { fclose(f); Py_DECREF(A); PyErr_SetString(PyExc_IOError, "error reading MatrixMarket data"); return NULL; }
+    if (SpMatrix_LLMatSetItem(A, i - 1, j - 1, v)) { fclose(f); Py_DECREF(A); return NULL; }
+  }
+  fclose(f);
+  return (PyObject *)A;
+}
+
+/* ---- pysparse_b200 additions: build csr_mat / sss_mat straight from arrays -- */
+static PyArrayObject *want(PyObject *o, int type) { return (PyArrayObject *)PyArray_FROM_OTF(o, type, NPY_ARRAY_IN_ARRAY); }
+
+static PyObject *csr_from_arrays(PyObject *self, PyObject *args)
+{
+  int m, n; PyObject *oi, *oc, *ov;
+  if (!PyArg_ParseTuple(args, "iiOOO", &m, &n, &oi, &oc, &ov)) return NULL;
+  PyArrayObject *ind = want(oi, NPY_INT32), *col = ind ? want(oc, NPY_INT32) : NULL, *val = col ? want(ov, NPY_DOUBLE) : NULL;
+  if (!val) { Py_XDECREF(ind); Py_XDECREF(col); return NULL; }
+  if (PyArray_SIZE(ind) != (npy_intp)m + 1 || PyArray_SIZE(col) != PyArray_SIZE(val)) {
+    Py_DECREF(ind); Py_DECREF(col); Py_DECREF(val);
+    PyErr_SetString(PyExc_ValueError, "csr_from_arrays: inconsistent array lengths");
+    return NULL;
+  }
+  CSRMatObject *op = PyObject_New(CSRMatObject, &CSRMatType);
+  if (!op) { Py_DECREF(ind); Py_DECREF(col); Py_DECREF(val); return PyErr_NoMemory(); }
+  op->dim[0] = m; op->dim[1] = n; op->nnz = (int)PyArray_SIZE(val); op->dev = NULL;
+  op->val = (double *)PyArray_DATA(val); op->col = (int *)PyArray_DATA(col); op->ind = (int *)PyArray_DATA(ind);
+  op->base[0] = (PyObject *)val; op->base[1] = (PyObject *)col; op->base[2] = (PyObject *)ind;
+  return (PyObject *)op;
+}
+
+static PyObject *sss_from_arrays(PyObject *self, PyObject *args)
+{
+  int n; PyObject *oi, *oc, *ov, *od;
+  if (!PyArg_ParseTuple(args, "iOOOO", &n, &oi, &oc, &ov, &od)) return NULL;
+  PyArrayObject *ind = want(oi, NPY_INT32), *col = ind ? want(oc, NPY_INT32) : NULL, *val = col ? want(ov, NPY_DOUBLE) : NULL,
+                *diag = val ? want(od, NPY_DOUBLE) : NULL;
+  if (!diag) { Py_XDECREF(ind); Py_XDECREF(col); Py_XDECREF(val); return NULL; }
+  if (PyArray_SIZE(ind) != (npy_intp)n + 1 || PyArray_SIZE(col) != PyArray_SIZE(val) || PyArray_SIZE(diag) != n) {
+    Py_DECREF(ind); Py_DECREF(col); Py_DECREF(val); Py_DECREF(diag);
+    PyErr_SetString(PyExc_ValueError, "sss_from_arrays: inconsistent array lengths");
+    return NULL;
+  }
+  SSSMatObject *op = PyObject_New(SSSMatObject, &SSSMatType);
+  if (!op) { Py_DECREF(ind); Py_DECREF(col); Py_DECREF(val); Py_DECREF(diag); return PyErr_NoMemory(); }
+  op->n = n; op->nnz = (int)PyArray_SIZE(val); op->dev = NULL;
+  op->val = (double *)PyArray_DATA(val); op->diag = (double *)PyArray_DATA(diag);
+  op->col = (int *)PyArray_DATA(col); op->ind = (int *)PyArray_DATA(ind);
+  op->base[0] = (PyObject *)val; op->base[1] = (PyObject *)diag; op->base[2] = (PyObject *)col; op->base[3] = (PyObject *)ind;
+  return (PyObject *)op;
+}
+
+static PyObject *not_on_hot_path(PyObject *self, PyObject *args)
+{
+  PyErr_SetString(PyExc_NotImplementedError,
+                  "sparse x sparse products (matrixmultiply / dot / symdot) are outside the SpMV / Krylov hot path "
+                  "pysparse_b200 accelerates (SURVEY.md section 8(f))");
+  return NULL;
+}
+
+static PyMethodDef spmatrix_methods[] = {
+  {"ll_mat", LLMat_zeros, METH_VARARGS, "ll_mat(n, m, sizeHint=1000, storeZeros=0)"},
+  {"ll_mat_sym", LLMat_sym_zeros, METH_VARARGS, "ll_mat_sym(n, sizeHint=1000, storeZeros=0)"},
+  {"ll_mat_from_mtx", LLMat_from_mtx, METH_VARARGS, "ll_mat_from_mtx(fileName)"},
+  {"matrixmultiply", not_on_hot_path, METH_VARARGS, NULL},
+  {"dot", not_on_hot_path, METH_VARARGS, NULL},
+  {"symdot", not_on_hot_path, METH_VARARGS, NULL},
+  {"csr_from_arrays", csr_from_arrays, METH_VARARGS, "csr_from_arrays(m, n, ind, col, val) -> csr_mat (pysparse_b200 addition)"},
+  {"sss_from_arrays", sss_from_arrays, METH_VARARGS, "sss_from_arrays(n, ind, col, val, diag) -> sss_mat (pysparse_b200 addition)"},
+  {NULL, NULL}
+};
+
+static void *SpMatrix_API[PSP_API_pointers];
+
+static struct PyModuleDef spmatrix_def = {PyModuleDef_HEAD_INIT, "spmatrix",
+  "pysparse_b200.sparse.spmatrix -- ll_mat / csr_mat / sss_mat with GPU matrix-vector products", -1, spmatrix_methods};
+
+static int init_type(PyTypeObject *t, const char *name, size_t size, destructor dealloc, PyMethodDef *methods,
+                     PyGetSetDef *getset, PyMappingMethods *mapping)
+{
+  t->tp_name = name;
+  t->tp_basicsize = (Py_ssize_t)size;
+  t->tp_dealloc = dealloc;
+  t->tp_flags = Py_TPFLAGS_DEFAULT;
+  t->tp_methods = methods;
+  t->tp_getset = getset;
+  t->tp_as_mapping = mapping;
+  return PyType_Ready(t);
+}
+
+PyMODINIT_FUNC PyInit_spmatrix(void)
+{
+  import_array();
+  static PyTypeObject zero = {PyVarObject_HEAD_INIT(NULL, 0)};
+  LLMatType = zero; CSRMatType = zero; SSSMatType = zero;
+  if (init_type(&LLMatType, "pysparse_b200.sparse.spmatrix.ll_mat", sizeof(LLMatObject), (destructor)LLMat_dealloc, LLMat_methods, LLMat_getset, &LLMat_as_mapping) < 0 ||
+      init_type(&CSRMatType, "pysparse_b200.sparse.spmatrix.csr_mat", sizeof(CSRMatObject), (destructor)CSRMat_dealloc, CSRMat_methods, CSRMat_getset, &CSRMat_as_mapping) < 0 ||
+      init_type(&SSSMatType, "pysparse_b200.sparse.spmatrix.sss_mat", sizeof(SSSMatObject), (destructor)SSSMat_dealloc, SSSMat_methods, SSSMat_getset, &SSSMat_as_mapping) < 0)
+    return NULL;
+  PyObject *m = PyModule_Create(&spmatrix_def);
+  if (!m) return NULL;
+  Py_INCREF(&LLMatType); PyModule_AddObject(m, "LLMatType", (PyObject *)&LLMatType);
+  Py_INCREF(&CSRMatType); PyModule_AddObject(m, "CSRMatType", (PyObject *)&CSRMatType);
+  Py_INCREF(&SSSMatType); PyModule_AddObject(m, "SSSMatType", (PyObject *)&SSSMatType);
+  SpMatrix_ErrorObject = PyUnicode_FromString("spmatrix.error");
+  PyModule_AddObject(m, "error", SpMatrix_ErrorObject);
+
+  SpMatrix_API[PSP_API_LLMatType] = (void *)&LLMatType;
+  SpMatrix_API[PSP_API_CSRMatType] = (void *)&CSRMatType;
+  SpMatrix_API[PSP_API_SSSMatType] = (void *)&SSSMatType;
+  SpMatrix_API[PSP_API_ParseVecOpArgs] = (void *)SpMatrix_ParseVecOpArgs;
+  SpMatrix_API[PSP_API_GetShape] = (void *)SpMatrix_GetShape;
+  SpMatrix_API[PSP_API_GetOrder] = (void *)SpMatrix_GetOrder;
+  SpMatrix_API[PSP_API_GetItem] = (void *)SpMatrix_GetItem;
+  SpMatrix_API[PSP_API_Matvec] = (void *)SpMatrix_Matvec;
+  SpMatrix_API[PSP_API_Precon] = (void *)SpMatrix_Precon;
+  SpMatrix_API[PSP_API_NewLLMatObject] = (void *)SpMatrix_NewLLMatObject;
+  SpMatrix_API[PSP_API_LLMatGetItem] = (void *)SpMatrix_LLMatGetItem;
+  SpMatrix_API[PSP_API_LLMatSetItem] = (void *)SpMatrix_LLMatSetItem;
+  SpMatrix_API[PSP_API_LLMatUpdateItemAdd] = (void *)SpMatrix_LLMatUpdateItemAdd;
+  SpMatrix_API[PSP_API_LLMatBuildColIndex] = (void *)SpMatrix_LLMatBuildColIndex;
+  SpMatrix_API[PSP_API_LLMatDestroyColIndex] = (void *)SpMatrix_LLMatDestroyColIndex;
+  SpMatrix_API[PSP_API_ItSolvers_Solve] = (void *)ItSolvers_Solve;
+  PyObject *cap = PyCapsule_New((void *)SpMatrix_API, PSP_CAPI_NAME, NULL);
+  if (!cap) return NULL;
+  PyModule_AddObject(m, "_C_API", cap);
+  return m;
+}

@@ -1,0 +1,173 @@
+"""GPU tests of the drop-in Python API: the reference's example scripts' call
+patterns (examples/poisson_test.py, ssor_test.py, poisson_gmres.py, tendigit.py,
+itsolvers_util.py __main__) run unchanged on pysparse_b200 and agree with the oracle."""
+import numpy as np
+import pytest
+
+from cases import build_matrix
+from helpers import load_kat
+
+pytestmark = pytest.mark.gpu
+KAT = {r["id"]: r for r in load_kat()}
+
+
+@pytest.fixture(scope="module")
+def mods(native):
+    if native.device_count() == 0:
+        pytest.fail("no CUDA device")
+    from pysparse.sparse import spmatrix
+    from pysparse.itsolvers import krylov
+    from pysparse.precon import precon
+    from pysparse.tools import poisson
+    return spmatrix, krylov, precon, poisson
+
+
+def test_poisson_test_example_flow(mods, checker):
+    """examples/poisson_test.py:62-135: SSS / CSR / LL matrices and SSOR give the same solve."""
+    spmatrix, krylov, precon, poisson = mods
+    n, tol = 100, 1e-8
+    L = poisson.poisson2d_sym(n)
+    A, S = L.to_csr(), L.to_sss()
+    b = np.ones(n * n)
+    g = KAT["p2d100_sss_pcg"]
+    sols = []
+    for M in (S, A, L):
+        x = np.zeros(n * n)
+        info, it, relres = krylov.pcg(M, b, x, tol, 2000)
+        assert (info, it) == (g["info"], g["iter"]) and abs(relres - g["relres"]) <= 1e-10
+        r = np.empty(n * n); M.matvec(x, r)
+        assert np.linalg.norm(b - r) <= 1.01 * tol * np.linalg.norm(b)
+        sols.append(x)
+    assert np.array_equal(sols[0], sols[1]) and np.array_equal(sols[0], sols[2])
+    x = np.zeros(n * n)
+    info, it, relres = krylov.pcg(S, b, x, tol, 2000, precon.ssor(S, 1.9))
+    g = KAT["p2d100_sss_pcg_ssor19"]
+    assert (info, it) == (g["info"], g["iter"]) and abs(relres - g["relres"]) <= 1e-10
+    K = precon.jacobi(L)              # the documented idiom: jacobi on the ll_mat, solve on the sss_mat
+    assert K.shape == (n * n, n * n)
+    x = np.zeros(n * n)
+    assert krylov.pcg(S, b, x, tol, 2000, K)[:2] == (0, 187)
+
+
+def test_config1_pcg_jacobi_n300(mods):
+    """BASELINE.json configs[0]: 2-D Poisson n=300 sss_mat, pcg + jacobi, tol 1e-10."""
+    spmatrix, krylov, precon, poisson = mods
+    g = build_matrix(["poisson2d", 300])
+    S = spmatrix.sss_from_arrays(g["n"], g["sss"][3], g["sss"][2], g["sss"][0], g["sss"][1])
+    x = np.zeros(g["n"])
+    info, it, relres = krylov.pcg(S, np.ones(g["n"]), x, 1e-10, 2000, precon.jacobi(S))
+    k = KAT["p2d300_sss_pcg_jacobi"]
+    assert info == 0 and abs(it - k["iter"]) <= 0.02 * k["iter"] and abs(relres - k["relres"]) <= 1e-10
+    assert abs(np.linalg.norm(x) - k["xnorm"]) <= 1e-8 * k["xnorm"]
+
+
+def test_all_solvers_oo_wrappers(mods):
+    """pysparse/itsolvers/itsolvers_util.py:154-178 (__main__ smoke) with asserts"""
+    spmatrix, krylov, precon, poisson = mods
+    import pysparse.itsolvers as its
+    L = poisson.poisson2d_sym(50)
+    A, S = L.to_csr(), L.to_sss()
+    n = 2500
+    b = np.ones(n)
+    for cls in (its.Pcg, its.Minres, its.Qmrs, its.Cgs, its.Bicgstab, its.Gmres):
+        for K in (None, precon.ssor(S), precon.jacobi(L, 1.0, 1)):
+            s = cls(A, precon=K)
+            x = np.full(n, 123.0)           # solve() zeroes x first (itsolvers_util.py:41)
+            info, it, relres = s.solve(b, x, 1e-8, 1000)
+            assert info == 0 and s.converged and s.itn == it and s.nofCalled == 1
+            r = np.empty(n); A.matvec(x, r)
+            assert np.linalg.norm(b - r) <= 2e-7 * np.linalg.norm(b), (cls.name, K)
+
+
+def test_x_updated_in_place_only_when_contiguous_float64(mods):
+    """itsolversmodule.c:70-82 (PyArray_AsCArray): a non-contiguous x is copied and the result lost."""
+    spmatrix, krylov, precon, poisson = mods
+    S = poisson.poisson2d_sym(10).to_sss()
+    b = np.ones(100)
+    x = np.zeros(100)
+    assert krylov.pcg(S, b, x, 1e-8, 100)[0] == 0 and np.any(x != 0)
+    xs = np.zeros(200)[::2]
+    assert krylov.pcg(S, b, xs, 1e-8, 100)[0] == 0 and not np.any(xs != 0)
+    assert krylov.pcg(S, [1.0] * 100, x, 1e-8, 100)[0] == 0       # b may be any sequence
+
+
+def test_duck_typed_matrix_and_preconditioner(mods):
+    """doc/pysparse/source/precon.rst:15-24: any object with shape + matvec / precon"""
+    spmatrix, krylov, precon, poisson = mods
+    L = poisson.poisson2d_sym(20)
+    S = L.to_sss()
+
+    class Shifted:
+        shape = S.shape
+
+        def matvec(self, x, y):
+            S.matvec(x, y)
+            y += 0.5 * x
+
+    class DiagPrec:
+        shape = S.shape
+
+        def precon(self, x, y):
+            y[:] = x / 4.5
+
+    x = np.zeros(400)
+    info, it, relres = krylov.pcg(Shifted(), np.ones(400), x, 1e-9, 500, DiagPrec())
+    assert info == 0
+    r = np.empty(400); Shifted().matvec(x, r)
+    assert np.linalg.norm(1.0 - r) <= 1e-8 * 20
+
+    class Bad:
+        shape = S.shape
+
+        def matvec(self, x, y):
+            raise KeyError("nope")
+
+    with pytest.raises(KeyError):
+        krylov.qmrs(Bad(), np.ones(400), np.zeros(400), 1e-8, 10)
+
+
+def test_precon_objects(mods, checker):
+    spmatrix, krylov, precon, poisson = mods
+    g = build_matrix(["random_sym", 1500, 8, 2])
+    n = g["n"]
+    S = spmatrix.sss_from_arrays(n, g["sss"][3], g["sss"][2], g["sss"][0], g["sss"][1])
+    So = checker.sss(n, *g["sss"])
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal(n)
+    for om, st in ((1.0, 1), (1.4, 2)):
+        K = precon.ssor(S, om, st)
+        y = np.empty(n); yo = np.zeros(n)
+        K.precon(x, y); checker.precon(checker.ssor(So, om, st), x, yo)
+        assert np.array_equal(y, yo) and K.shape == (n, n) and K.levels[0] >= 1
+        with pytest.raises(ValueError, match="contiguous"):
+            K.precon(x[::2], y)
+    J = precon.jacobi(S, 0.8, 3)
+    y = np.empty(n); yo = np.zeros(n)
+    J.precon(x, y); checker.precon(checker.jacobi(So, g["sss"][1], 0.8, 3), x, yo)
+    assert np.max(np.abs(y - yo)) <= 1e-13 * np.max(np.abs(yo))
+    assert np.array_equal(x, x)      # x unchanged
+
+
+def test_tendigit_known_answer(mods):
+    """examples/tendigit.py:26-49 -- Trefethen's 100-digit challenge, problem 7:
+    x[0] of A x = e_0 is 0.7250783462684011..."""
+    spmatrix, krylov, precon, poisson = mods
+    g = build_matrix(["tendigit", 20000])
+    n = g["n"]
+    S = spmatrix.sss_from_arrays(n, g["sss"][3], g["sss"][2], g["sss"][0], g["sss"][1])
+    b = np.zeros(n); b[0] = 1.0
+    x = np.zeros(n)
+    info, it, relres = krylov.minres(S, b, x, 1e-16, n, precon.ssor(S))
+    assert abs(x[0] - 0.7250783462684011) <= 1e-14
+
+
+def test_llmat_device_cache_tracks_modifications(mods):
+    spmatrix, krylov, precon, poisson = mods
+    L = poisson.poisson2d(6)
+    x = np.arange(36, dtype=float); y1 = np.empty(36); y2 = np.empty(36)
+    L.matvec(x, y1)
+    L[0, 0] = 10.0
+    L.matvec(x, y2)
+    assert y2[0] == y1[0] + 6.0 * x[0] and np.array_equal(y1[1:], y2[1:])
+    yt = np.empty(36); L.matvec_transp(x, yt)
+    assert np.allclose(yt, y2)

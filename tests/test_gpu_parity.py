@@ -46,7 +46,8 @@ def test_spmv_and_precon_kernels_vs_golden(gpu, native, kc, variant):
         assert relmax(y, G[key + "/csr_y"]) <= SPMV_TOL
         yt = np.full(shape[1], np.nan); gpu.matvec(A, xt, yt, transp=True)
         assert relmax(yt, G[key + "/csr_yt"]) <= SPMV_TOL
-        if key not in ("pow_3000",):     # short rows keep the reference's summation order
+        # row blocks averaging <= 16 entries per row keep the reference's summation order
+        if key not in ("pow_3000", "tendigit_500"):
             assert np.array_equal(y, G[key + "/csr_y"]) and np.array_equal(yt, G[key + "/csr_yt"])
         if "sss" in mat:
             S = gpu.sss(n, *mat["sss"])
