@@ -183,6 +183,47 @@ int psp_event_elapsed_ms(int start, int stop, double *ms);
  * sampling to every `sample_every`-th SpMV launch (0 = off, the default). */
 int psp_spmv_timing(int sample_every, int *count, double *total_ms);
 
+/* ---- multi-GPU (one process per GPU; not in the reference) --
+ *
+ * Rows are sharded in contiguous blocks: rank r owns rows
+ * [rowptr[r], rowptr[r+1]) of A and the same slices of every vector.  Work
+ * vectors live in a symmetric heap that all ranks of the node map through
+ * CUDA IPC; halo values are pulled from the owners over NVLink and scalar
+ * all-reduces happen inside the reduction kernels through peer mailboxes.
+ * The launcher (torchrun + torch.distributed in bench.py / tests) only
+ * all-gathers the 128-byte IPC handle blobs. */
+typedef struct psp_dmat psp_dmat;   /* this rank's row slab of a sharded CSR matrix */
+
+/* Host-only planning of one rank's slab (bit-exact integer work, no GPU
+ * needed): given the row partition and the slab's CSR with GLOBAL column
+ * indices, produce the local column numbering (own columns first, then the
+ * halo columns in ascending global order), and for every halo column its
+ * global index, owner rank and index inside the owner's slab.  The output
+ * arrays may be NULL; halo arrays need room for up to nnz entries. */
+int psp_dist_plan(int world, int rank, const int *rowptr, int nl, const int *ind,
+                  const int *col_global, int *col_local, int *halo_gcol, int *halo_owner,
+                  int *halo_ridx, int *nhalo_out);
+
+/* Allocate this rank's symmetric heap (nslots vectors of slot_elems doubles)
+ * and control block; writes two CUDA IPC handles (128 bytes) to handles_out. */
+int psp_dist_init(int rank, int world, size_t slot_elems, int nslots, void *handles_out);
+/* all_handles: the world x 128-byte blobs of all ranks, in rank order */
+int psp_dist_connect(const void *all_handles);
+int psp_dist_shutdown(void);
+int psp_dist_info(int *rank, int *world, size_t *slot_elems, int *nslots);
+
+/* This rank's slab: ind[nl+1], col_global[nnz], val[nnz] */
+int psp_dist_csr_create(const int *rowptr, int nnz, const int *ind, const int *col_global,
+                        const double *val, psp_dmat **out);
+void psp_dist_mat_destroy(psp_dmat *a);
+int psp_dist_mat_info(const psp_dmat *a, int *nl, int *nhalo, unsigned *neighbour_mask);
+
+/* Sharded solve (PSP_PCG; K = NULL or a single-step Jacobi built from the local
+ * diagonal).  db / dx are this rank's slices, device-resident.  Collective:
+ * every rank must call it with the same tol / maxit. */
+int psp_dist_solve_dev(int solver, psp_dmat *A, psp_prec *K, const double *db, double *dx,
+                       double tol, int maxit, int *info, int *iter, double *relres);
+
 /* ---- tuning knobs (default to reference semantics) --------------------- */
 /* name: "spmv_variant" (0 auto, 1 scalar-stream, 2 vector-stream ...),
  *       "poll_chunk" (iterations enqueued between convergence polls),

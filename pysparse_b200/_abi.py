@@ -29,6 +29,8 @@ SYMBOLS = [
     "psp_prec_apply_dev", "psp_ssor_levels",
     "psp_solve", "psp_solve_dev", "psp_last_device_ms", "psp_set_option", "psp_get_option",
     "psp_event_record", "psp_event_elapsed_ms", "psp_spmv_timing",
+    "psp_dist_plan", "psp_dist_init", "psp_dist_connect", "psp_dist_shutdown", "psp_dist_info",
+    "psp_dist_csr_create", "psp_dist_mat_destroy", "psp_dist_mat_info", "psp_dist_solve_dev",
 ]
 
 SOLVERS = {"pcg": 0, "minres": 1, "qmrs": 2, "bicgstab": 3, "cgs": 4, "gmres": 5}

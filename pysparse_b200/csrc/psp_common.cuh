@@ -40,7 +40,41 @@ constexpr int kThreads = 256;
 // duration of a solve; every kernel of the solve reads `done` first and
 // returns immediately when it is set, so iterations enqueued past the point
 // of convergence cost a few microseconds and change nothing.
+// ---- multi-GPU device-side structures (psp_dist.cu) ------------------------
+// One process per GPU; every rank maps every peer's "symmetric heap" and
+// control block through CUDA IPC, so that
+//   * scalar all-reduces are done INSIDE the reduction kernels: the last block
+//     pushes its partial sums into every peer's mailbox (NVLink stores) and
+//     sums the W mailbox entries it receives, in rank order -- the same bits
+//     on every rank, no NCCL launch, no host involvement;
+//   * x-halo values are pulled straight out of the neighbours' vectors by a
+//     small gather kernel (NVLink loads) once the owner has published them.
+constexpr int kMaxRanks = 8;
+constexpr int kMailRing = 4;
+
+struct DistMail {                       // one all-reduce contribution
+  double val[kRedSlots + 1];            // sums, then the max
+  unsigned long long seq;               // written last (release); reduction sequence number
+  unsigned long long pad[6];
+};
+
+struct DistCtl {                        // lives in each rank's IPC-shared control block
+  unsigned long long pub;               // number of vector publications completed by this rank
+  unsigned long long pad[15];
+  DistMail mail[kMailRing][kMaxRanks];  // mail[seq % ring][source rank]
+};
+
+struct DistDev {                        // device-resident descriptor (private to the rank)
+  int rank, world;
+  DistCtl *ctl[kMaxRanks];              // ctl[rank] is local, the others are peer mappings
+  double *heap[kMaxRanks];              // symmetric heaps (same layout on every rank)
+  unsigned long long red_seq;           // reductions performed so far (identical on all ranks)
+  unsigned long long pubs_done;         // publications performed by this rank
+  unsigned long long pulls_done;        // halo pulls performed by this rank
+};
+
 struct State {
+  DistDev *dist; // nullptr on a single GPU
   int done;      // 1: solve finished, remaining kernels are no-ops
   int info;      // solver flag / info as the reference reports it
   int iter;      // iteration count as the reference reports it
@@ -163,11 +197,74 @@ __device__ __forceinline__ double block_max(double v, double *sh) {
 // partials[s * kMaxGrid + blockIdx.x]; the block that draws the last ticket
 // adds them up in a fixed order (independent of which block that is) and
 // returns true in ALL its threads with totals[] valid in thread 0.
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double *p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_f64(double *p, double v) {
+  asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+
+// Cross-GPU part of a reduction, run by the LAST block of the reduction kernel
+// on every rank: lanes 0..W-1 push this rank's totals into rank w's mailbox
+// (remote NVLink stores, value first, sequence number last with release
+// semantics), then wait for rank w's contribution in the local mailbox and the
+// sums are formed in rank order, so every rank gets bit-identical results.
+template <int NS, bool HASMAX>
+__device__ __forceinline__ void dist_allreduce(DistDev *dd, double *totals, double *totmax, double *sh) {
+  __shared__ double box[kMaxRanks][kRedSlots + 1];
+  const int W = dd->world, me = dd->rank;
+  const unsigned long long seq = dd->red_seq + 1;
+  const int slot = (int)(seq % kMailRing);
+  __syncthreads();
+  if ((int)threadIdx.x < W) {
+    const int w = threadIdx.x;
+    DistMail *dst = &dd->ctl[w]->mail[slot][me];
+#pragma unroll
+    for (int s = 0; s < NS; s++) st_relaxed_sys_f64(&dst->val[s], totals[s]);
+    if (HASMAX) st_relaxed_sys_f64(&dst->val[kRedSlots], *totmax);
+    st_release_sys(&dst->seq, seq);
+    const DistMail *src = &dd->ctl[me]->mail[slot][w];
+    while (ld_acquire_sys(&src->seq) != seq) { }
+#pragma unroll
+    for (int s = 0; s < NS; s++) box[w][s] = ld_relaxed_sys_f64(&src->val[s]);
+    if (HASMAX) box[w][kRedSlots] = ld_relaxed_sys_f64(&src->val[kRedSlots]);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+      double a = 0.0;
+      for (int w = 0; w < W; w++) a += box[w][s];
+      totals[s] = a;
+    }
+    if (HASMAX) {
+      double a = 0.0;
+      for (int w = 0; w < W; w++) a = fmax(a, box[w][kRedSlots]);
+      *totmax = a;
+    }
+    dd->red_seq = seq;
+  }
+  (void)sh;
+}
+
 template <int NS, bool HASMAX>
 __device__ __forceinline__ bool grid_reduce_finish(const double *mine, double mymax,
                                                    double *partials, unsigned *ticket,
-                                                   double *totals, double *totmax, double *sh) {
+                                                   double *totals, double *totmax, double *sh,
+                                                   DistDev *dd = nullptr) {
   __shared__ bool is_last;
+  __shared__ double tot_sh[kRedSlots + 1];
+  __syncthreads();   // every thread's global stores precede thread 0's fence + ticket
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int s = 0; s < NS; s++) partials[s * kMaxGrid + blockIdx.x] = mine[s];
@@ -195,6 +292,19 @@ __device__ __forceinline__ bool grid_reduce_finish(const double *mine, double my
     if (threadIdx.x == 0) *totmax = a;
   }
   if (threadIdx.x == 0) *ticket = 0u;  // re-arm for the next kernel (stream-ordered)
+  if (dd != nullptr && (NS > 0 || HASMAX)) {
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int s = 0; s < NS; s++) tot_sh[s] = totals[s];
+      if (HASMAX) tot_sh[kRedSlots] = *totmax;
+    }
+    dist_allreduce<NS, HASMAX>(dd, tot_sh, &tot_sh[kRedSlots], sh);
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int s = 0; s < NS; s++) totals[s] = tot_sh[s];
+      if (HASMAX) *totmax = tot_sh[kRedSlots];
+    }
+  }
   return true;
 }
 

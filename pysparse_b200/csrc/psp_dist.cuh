@@ -1,0 +1,29 @@
+// psp_dist.cuh -- host-side structures of the multi-GPU layer.
+#pragma once
+#include "psp_mat.cuh"
+
+namespace psp {
+
+struct DistHost {
+  bool ready = false;
+  int rank = 0, world = 1;
+  size_t slot_elems = 0;
+  int nslots = 0;
+  double *heap = nullptr;                 // local symmetric heap: nslots x slot_elems doubles
+  DistCtl *ctl = nullptr;                 // local control block (publication counter + mailboxes)
+  double *peer_heap[kMaxRanks] = {};
+  DistCtl *peer_ctl[kMaxRanks] = {};
+  DistDev *dev = nullptr;                 // device copy of the descriptor
+};
+
+struct DistMat {
+  psp_mat *local = nullptr;               // nl x (nl + nhalo) CSR, halo columns appended
+  int nl = 0, nhalo = 0, nglobal = 0;
+  int *d_owner = nullptr, *d_ridx = nullptr;
+  unsigned nbmask = 0;                    // ranks this rank pulls halo values from
+};
+
+DistHost &dist();
+int dist_pull(DistMat *dm, double *xloc);
+
+}  // namespace psp

@@ -11,6 +11,7 @@
 // vectors through pinned host memory around each callback.
 #include "psp_mat.cuh"
 #include "psp_vec.cuh"
+#include "psp_dist.cuh"
 
 namespace psp {
 
@@ -80,6 +81,9 @@ struct Solve {
   // fused identity / Jacobi(steps == 1) preconditioner: z = r .* dinv (dinv == nullptr: z = r)
   bool fusedK = false;
   const double *dinv = nullptr;
+  // multi-GPU: A is this rank's row slab; work vectors live in the symmetric heap
+  DistMat *dm = nullptr;
+  long vstride = 0;          // distance between work vectors (0: n)
 };
 
 static int read_done(Solve &s, int *done) {
@@ -115,6 +119,15 @@ static int apply_callback(Solve &s, const Op &op, const double *dx, double *dy, 
 static int apply_A(Solve &s, const double *dx, double *dy, const double *w1 = nullptr,
                    const double *w2 = nullptr, bool w2_is_y = false, int epilogue = EPI_NONE,
                    int gate = 0) {
+  if (s.dm) {
+    // dx is a heap vector its producer has published: fetch the halo entries from the
+    // neighbours' copies (NVLink), then multiply with the local slab
+    PSP_TRY(dist_pull(s.dm, const_cast<double *>(dx)));
+    SpmvDots d;
+    d.w1 = w1; d.w2 = w2; d.w2_is_y = w2_is_y ? 1 : 0; d.epilogue = epilogue; d.S = s.S;
+    d.gate = gate;
+    return spmv_launch(s.dm->local, dx, dy, d);
+  }
   if (s.A.mat) {
     SpmvDots d;
     d.w1 = w1; d.w2 = w2; d.w2_is_y = w2_is_y ? 1 : 0; d.epilogue = epilogue; d.S = s.S;
@@ -217,18 +230,25 @@ struct FPcgUpdate {         // stagnation scan, x += alpha p, r -= alpha q, |r|^
 
 static int solve_pcg(Solve &s, const double *b, double *x, double *work) {
   const long n = s.n;
-  double *r = work, *z = work + n, *p = work + 2 * n, *q = work + 3 * n;
+  const long vs = s.vstride ? s.vstride : n;
+  double *r = work, *z = work + vs, *p = work + 2 * vs, *q = work + 3 * vs;
+  const int pub = s.dm ? kPublish : 0;     // multi-GPU: p is read by the neighbours
   PSP_TRY(launch_map(FNormSq{b}, n, EPI_PCG_NORMB));
-  PSP_TRY(apply_A(s, x, r));
+  if (s.dm) {
+    PSP_TRY(launch_map(FCopy{x, p}, n, EPI_NONE, pub));   // x0 into the shared heap, published
+    PSP_TRY(apply_A(s, p, r));
+  } else {
+    PSP_TRY(apply_A(s, x, r));
+  }
   PSP_TRY(launch_map(FPcgResid{b, r, x, s.dinv, 0}, n, s.fusedK ? EPI_PCG_RESID0_J : EPI_PCG_RESID0));
-  const bool sync_each = !(s.A.mat && (s.fusedK || s.K.prec));
+  const bool sync_each = !((s.A.mat || s.dm) && (s.fusedK || s.K.prec));
   auto body = [&](long long) -> int {
     if (s.fusedK) {
-      PSP_TRY(launch_map(FPcgP{r, s.dinv, p, 0.0, 0}, n));
+      PSP_TRY(launch_map(FPcgP{r, s.dinv, p, 0.0, 0}, n, EPI_NONE, pub));
     } else {
       PSP_TRY(apply_K(s, r, z));
       PSP_TRY(launch_map(FDot{r, z}, n, EPI_PCG_RHO));
-      PSP_TRY(launch_map(FPcgP{z, nullptr, p, 0.0, 0}, n));
+      PSP_TRY(launch_map(FPcgP{z, nullptr, p, 0.0, 0}, n, EPI_NONE, pub));
     }
     PSP_TRY(apply_A(s, p, q, p, nullptr, false, EPI_PCG_PQ));
     PSP_TRY(launch_map(FPcgUpdate{p, q, s.fusedK ? s.dinv : nullptr, x, r, 0.0, 0}, n,
@@ -769,9 +789,62 @@ int solve_dev(int solver, const psp_operator *Aop, const psp_operator *Kop, int 
   return PSP_OK;
 }
 
+// Distributed solve: this rank's row slab, vectors in the symmetric heap.  The
+// kernels are the single-GPU ones; reductions are all-reduced in-kernel and
+// the multiplied vector's halo is pulled from the neighbours (psp_dist.cu).
+int dist_solve_dev(int solver, DistMat *dm, psp_prec *K, const double *db, double *dx, double tol,
+                   int maxit, int *info, int *iter, double *relres) {
+  PSP_TRY(ensure_init());
+  Ctx &c = ctx();
+  DistHost &d = dist();
+  if (!d.ready || !dm) { set_error("psp_dist_solve_dev: distributed layer not initialised"); return PSP_ERR_DIST; }
+  if (solver != PSP_PCG) { set_error("psp_dist_solve_dev: only PCG is sharded in this release"); return PSP_ERR_ARG; }
+  if (K && !(K->kind == 1 && K->steps == 1 && K->n == dm->nl)) {
+    set_error("psp_dist_solve_dev: preconditioner must be None or single-step Jacobi on the local rows");
+    return PSP_ERR_ARG;
+  }
+  if (d.nslots < 4) { set_error("psp_dist_solve_dev: symmetric heap has fewer than 4 slots"); return PSP_ERR_ARG; }
+  Solve s;
+  s.n = dm->nl;
+  s.S = c.state;
+  s.dm = dm;
+  s.vstride = (long)d.slot_elems;
+  s.fusedK = true;
+  s.dinv = K ? K->d_dinv : nullptr;
+  s.K.present = (K != nullptr);
+  s.K.prec = K;
+  State init;
+  memset(&init, 0, sizeof init);
+  init.dist = d.dev;
+  init.maxit = maxit; init.tol = tol; init.iter = -1; init.relres = nan("");
+  c.h_state[0] = init;
+  c.h_state[1] = init;
+  PSP_CUDA(cudaMemcpyAsync(c.state, &c.h_state[0], sizeof(State), cudaMemcpyHostToDevice, c.stream));
+  PSP_CUDA(cudaStreamSynchronize(c.stream));
+  PSP_CUDA(cudaEventRecord(c.ev0, c.stream));
+  int st = solve_pcg(s, db, dx, d.heap);
+  if (st != PSP_OK) { cudaStreamSynchronize(c.stream); return st; }
+  PSP_CUDA(cudaEventRecord(c.ev1, c.stream));
+  PSP_CUDA(cudaMemcpyAsync(&c.h_state[0], c.state, sizeof(State), cudaMemcpyDeviceToHost, c.stream));
+  PSP_CUDA(cudaStreamSynchronize(c.stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, c.ev0, c.ev1);
+  c.last_ms = ms;
+  const State &R = c.h_state[0];
+  if (info) *info = R.info;
+  if (iter) *iter = R.iter;
+  if (relres) *relres = R.relres;
+  return PSP_OK;
+}
+
 }  // namespace psp
 
 using namespace psp;
+
+extern "C" int psp_dist_solve_dev(int solver, psp_dmat *A, psp_prec *K, const double *db, double *dx,
+                                  double tol, int maxit, int *info, int *iter, double *relres) {
+  return dist_solve_dev(solver, (DistMat *)A, K, db, dx, tol, maxit, info, iter, relres);
+}
 
 extern "C" int psp_solve_dev(int solver, const psp_operator *A, const psp_operator *K, int n,
                              const double *db, double *dx, double tol, int maxit, int gmres_dim,

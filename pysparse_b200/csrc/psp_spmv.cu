@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_spmv_stream(SpmvArgs a) {
     mine[0] = block_sum(acc0, red_sh);
     mine[1] = block_sum(acc1, red_sh);
     double tot[2], dummy;
-    if (grid_reduce_finish<2, false>(mine, 0.0, a.partials, a.ticket, tot, &dummy, red_sh)) {
+    if (grid_reduce_finish<2, false>(mine, 0.0, a.partials, a.ticket, tot, &dummy, red_sh, a.S->dist)) {
       if (tid == 0) {
         a.S->red[0] = tot[0];
         a.S->red[1] = tot[1];
@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(kThreads) k_spmv_tma(SpmvArgs a) {
     mine[0] = block_sum(acc0, red_sh);
     mine[1] = block_sum(acc1, red_sh);
     double tot[2], dummy;
-    if (grid_reduce_finish<2, false>(mine, 0.0, a.partials, a.ticket, tot, &dummy, red_sh)) {
+    if (grid_reduce_finish<2, false>(mine, 0.0, a.partials, a.ticket, tot, &dummy, red_sh, a.S->dist)) {
       if (tid == 0) {
         a.S->red[0] = tot[0];
         a.S->red[1] = tot[1];

@@ -6,6 +6,11 @@
 // (psp_epilogue.cuh) runs once the grid-wide sums are known.  This is what
 // replaces the reference's sequences of ddot / daxpy / dcopy / dnrm2 calls
 // (pysparse/include/blas.h:97-126) with one pass over memory per phase.
+//
+// Multi-GPU: when State::dist is set, the sums are all-reduced across the
+// ranks inside the same kernel (dist_allreduce, psp_common.cuh), and a kernel
+// launched with kPublish announces -- after all its stores -- that the vector it
+// produced may now be read by the peers (halo pull, psp_dist.cu).
 #pragma once
 #include "psp_common.cuh"
 #include "psp_epilogue.cuh"
@@ -14,12 +19,25 @@ namespace psp {
 
 // gate: 0 = skip when S->done; 1 = also skip when S->cyc_done (GMRES inner
 // loop); 3 = never skip.
+constexpr int kGateMask = 0xff;
+constexpr int kPublish = 0x100;
+
 __device__ __forceinline__ bool gated_out(const State *S, int gate) {
+  gate &= kGateMask;
   if (gate == 3) return false;   // runs unconditionally (post-loop clean-up kernels)
   const volatile State *V = S;
   if (V->done) return true;
   if (gate == 1 && V->cyc_done) return true;
   return false;
+}
+
+// Announce to the peers that this rank's freshly written vector is complete.
+// Called by thread 0 of the last block (all blocks' stores are ordered before
+// the ticket it drew).
+__device__ __forceinline__ void dist_publish(DistDev *dd) {
+  __threadfence_system();
+  dd->pubs_done += 1;
+  st_release_sys(&dd->ctl[dd->rank]->pub, dd->pubs_done);
 }
 
 // F must provide:
@@ -41,19 +59,21 @@ __global__ void __launch_bounds__(kThreads) k_map(F f, long n, State *S, double 
   double mx = 0.0;
   const long stride = (long)gridDim.x * blockDim.x;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) f.elem(i, acc, mx);
-  if constexpr (F::NS > 0 || F::HASMAX || F::TICKET) {
+  const bool publish = (gate & kPublish) != 0;
+  if (F::NS > 0 || F::HASMAX || F::TICKET || publish) {
     double mine[NA];
 #pragma unroll
     for (int s = 0; s < F::NS; s++) mine[s] = block_sum(acc[s], sh);
     double mymax = 0.0;
     if constexpr (F::HASMAX) mymax = block_max(mx, sh);
     double tot[NA], totmax = 0.0;
-    if (grid_reduce_finish<F::NS, F::HASMAX>(mine, mymax, partials, ticket, tot, &totmax, sh)) {
+    if (grid_reduce_finish<F::NS, F::HASMAX>(mine, mymax, partials, ticket, tot, &totmax, sh, S->dist)) {
       if (threadIdx.x == 0) {
 #pragma unroll
         for (int s = 0; s < F::NS; s++) S->red[s] = tot[s];
         if constexpr (F::HASMAX) S->redmax = totmax;
         run_epilogue(epilogue, S, (void *)(S + 1));
+        if (publish && S->dist) dist_publish(S->dist);
       }
     }
   }

@@ -20,7 +20,7 @@ import numpy as np
 
 
 def _stencil(dims, offsets_lower, w_lower, w_diag, w_upper, want_csr=True, want_sss=True,
-             chunk_rows=1 << 22):
+             chunk_rows=1 << 22, rows=None):
     """Generic structured-grid builder.  ``dims`` = (n0, n1, ...) with index
     k = i0 + n0*i1 + n0*n1*i2...; neighbour d along axis a exists iff the
     coordinate stays inside the grid.  ``offsets_lower`` is implied: axis a has
@@ -40,12 +40,16 @@ def _stencil(dims, offsets_lower, w_lower, w_diag, w_upper, want_csr=True, want_
             cs.append((k // strides[a]) % dims[a])
         return cs
 
-    # per-row counts first (cheap closed form through coordinates, chunked)
+    # `rows = (a, b)`: only rows a..b-1 are generated (a row slab for one GPU); column
+    # indices stay GLOBAL and the row pointer is relative to the slab.
+    ra, rb = (0, N) if rows is None else (int(rows[0]), int(rows[1]))
+    nloc = rb - ra
+    out["rows"] = (ra, rb)
     csr_parts, sss_parts = [], []
-    csr_cnt = np.empty(N, dtype=np.int32) if want_csr else None
-    sss_cnt = np.empty(N, dtype=np.int32) if want_sss else None
-    for r0 in range(0, N, chunk_rows):
-        r1 = min(N, r0 + chunk_rows)
+    csr_cnt = np.empty(nloc, dtype=np.int32) if want_csr else None
+    sss_cnt = np.empty(nloc, dtype=np.int32) if want_sss else None
+    for r0 in range(ra, rb, chunk_rows):
+        r1 = min(rb, r0 + chunk_rows)
         k = np.arange(r0, r1, dtype=np.int64)
         cs = coords(k)
         # column slots in ascending column order: lower axes descending, diag, upper ascending
@@ -64,24 +68,26 @@ def _stencil(dims, offsets_lower, w_lower, w_diag, w_upper, want_csr=True, want_
         Cc = np.stack(cols, axis=1)
         Vv = np.broadcast_to(np.asarray(vals, dtype=np.float64), M.shape)
         if want_csr:
-            csr_cnt[r0:r1] = M.sum(axis=1)
+            csr_cnt[r0 - ra:r1 - ra] = M.sum(axis=1)
             csr_parts.append((Vv[M], Cc[M].astype(np.int32)))
         if want_sss:
             Ml = M[:, :nlow]
-            sss_cnt[r0:r1] = Ml.sum(axis=1)
+            sss_cnt[r0 - ra:r1 - ra] = Ml.sum(axis=1)
             sss_parts.append((Vv[:, :nlow][Ml], Cc[:, :nlow][Ml].astype(np.int32)))
     if want_csr:
-        ind = np.zeros(N + 1, dtype=np.int64)
+        ind = np.zeros(nloc + 1, dtype=np.int64)
         np.cumsum(csr_cnt, out=ind[1:])
         assert ind[-1] < 2**31
-        out["csr"] = (np.concatenate([p[0] for p in csr_parts]),
-                      np.concatenate([p[1] for p in csr_parts]), ind.astype(np.int32))
+        out["csr"] = (np.concatenate([p[0] for p in csr_parts]) if csr_parts else np.zeros(0),
+                      np.concatenate([p[1] for p in csr_parts]) if csr_parts else np.zeros(0, np.int32),
+                      ind.astype(np.int32))
     if want_sss:
-        ind = np.zeros(N + 1, dtype=np.int64)
+        ind = np.zeros(nloc + 1, dtype=np.int64)
         np.cumsum(sss_cnt, out=ind[1:])
-        out["sss"] = (np.concatenate([p[0] for p in sss_parts]),
-                      np.full(N, float(w_diag)),
-                      np.concatenate([p[1] for p in sss_parts]), ind.astype(np.int32))
+        out["sss"] = (np.concatenate([p[0] for p in sss_parts]) if sss_parts else np.zeros(0),
+                      np.full(nloc, float(w_diag)),
+                      np.concatenate([p[1] for p in sss_parts]) if sss_parts else np.zeros(0, np.int32),
+                      ind.astype(np.int32))
     return out
 
 

@@ -1,0 +1,69 @@
+"""Multi-GPU parity check (run under torchrun on a >= 2-GPU box):
+sharded PCG + Jacobi vs the single-GPU solve and the CPU oracle."""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.distributed as dist
+
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+os.environ["PSP_DEVICE"] = str(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+ctl = dist.new_group(backend="gloo")
+from pysparse_b200 import _abi as P
+from pysparse_b200 import dist as D
+from pysparse_b200.tools import gallery as g
+import oracle
+
+ok = True
+first = True
+for n, tol in ((24, 1e-10), (48, 1e-10)):
+    N = n ** 3
+    rowptr = D.row_partition(N, world, align=n * n)
+    r0, r1 = int(rowptr[rank]), int(rowptr[rank + 1])
+    slab = g.poisson3d(n, want_sss=False, rows=(r0, r1))
+    val, col, ind = slab["csr"]
+    nl = r1 - r0
+    if first:
+        D.init(rank, world, 48 ** 3 // world + 2 * 48 * 48 + 64, nslots=4, group=ctl)
+        first = False
+    A = D.ShardedMatrix(rowptr, ind, col, val)
+    K = P.Precon.jacobi(None, np.full(nl, 6.0))
+    db = P.DeviceVector(nl, np.ones(nl)); dx = P.DeviceVector(nl, np.zeros(nl))
+    res = D.pcg(A, db, dx, tol, 2000, K)
+    xl = dx.download()
+    parts = [None] * world
+    dist.all_gather_object(parts, xl, group=ctl)
+    x = np.concatenate(parts)
+    if rank == 0:
+        full = g.poisson3d(n)
+        ora = oracle.Oracle("ref") if oracle.have_ref() else oracle.Oracle("port")
+        Ao = ora.csr(N, N, *full["csr"]); Ko = ora.jacobi(Ao, np.full(N, 6.0))
+        xo = np.zeros(N)
+        ro = ora.solve("pcg", Ao, np.ones(N), xo, tol, 2000, Ko)
+        A1 = P.Matrix.csr(N, N, *full["csr"]); K1 = P.Precon.jacobi(None, np.full(N, 6.0))
+        x1 = np.zeros(N)
+        r1g = P.solve("pcg", A1, np.ones(N), x1, tol, 2000, K1)
+        good = (res[0] == ro[0] == 0 and abs(res[1] - ro[1]) <= max(1, 0.02 * ro[1]) and abs(res[2] - ro[2]) <= 1e-10
+                and np.max(np.abs(x - xo)) <= 1e-8 * np.max(np.abs(xo)))
+        print(f"n={n} world={world}: sharded={res} single_gpu={r1g} oracle={ro} "
+              f"max|x-x_oracle|={np.max(np.abs(x - xo)):.2e} {'OK' if good else 'FAIL'}", flush=True)
+        ok = ok and good
+    # a second solve on the same handles (sequence numbers keep counting)
+    dx.fill(0.0)
+    res2 = D.pcg(A, db, dx, tol, 2000, K)
+    if res2 != res:
+        print(f"rank {rank}: repeated solve differs: {res} vs {res2}", flush=True)
+        ok = False
+    del A
+flags = [None] * world
+dist.all_gather_object(flags, ok, group=ctl)
+D.shutdown()
+dist.destroy_process_group()
+if rank == 0:
+    print("DIST CHECK", "PASSED" if all(flags) else "FAILED", flush=True)
+sys.exit(0 if all(flags) else 1)
