@@ -218,11 +218,13 @@ int psp_dist_csr_create(const int *rowptr, int nnz, const int *ind, const int *c
 void psp_dist_mat_destroy(psp_dmat *a);
 int psp_dist_mat_info(const psp_dmat *a, int *nl, int *nhalo, unsigned *neighbour_mask);
 
-/* Sharded solve (PSP_PCG; K = NULL or a single-step Jacobi built from the local
- * diagonal).  db / dx are this rank's slices, device-resident.  Collective:
- * every rank must call it with the same tol / maxit. */
+/* Sharded solve (PSP_PCG, PSP_BICGSTAB, PSP_GMRES; K = NULL or a single-step
+ * Jacobi built from the local diagonal).  db / dx are this rank's slices,
+ * device-resident.  Collective: every rank must call it with the same
+ * arguments.  Heap slots needed: 4 (pcg), 8 (bicgstab), 2*dim+2 (gmres with
+ * Jacobi) or dim+2 (gmres without preconditioner). */
 int psp_dist_solve_dev(int solver, psp_dmat *A, psp_prec *K, const double *db, double *dx,
-                       double tol, int maxit, int *info, int *iter, double *relres);
+                       double tol, int maxit, int gmres_dim, int *info, int *iter, double *relres);
 
 /* ---- tuning knobs (default to reference semantics) --------------------- */
 /* name: "spmv_variant" (0 auto, 1 scalar-stream, 2 vector-stream ...),

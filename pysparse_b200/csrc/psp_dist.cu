@@ -25,8 +25,8 @@ DistHost &dist() { return g_dist; }
 
 __global__ void __launch_bounds__(kThreads) k_halo_pull(State *S, size_t slot_off, const int *owner,
                                                         const int *ridx, int nhalo, int nl, double *xloc,
-                                                        unsigned nbmask, unsigned *ticket) {
-  if (*(const volatile int *)&S->done) return;
+                                                        unsigned nbmask, unsigned *ticket, int gate) {
+  if (gated_out(S, gate)) return;
   DistDev *dd = S->dist;
   __shared__ bool is_last;
   if (threadIdx.x == 0) {
@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(kThreads) k_halo_pull(State *S, size_t slot_of
   }
 }
 
-int dist_pull(DistMat *dm, double *xloc) {
+int dist_pull(DistMat *dm, double *xloc, int gate) {
   Ctx &c = ctx();
   DistHost &d = g_dist;
   int grid = (dm->nhalo + kThreads - 1) / kThreads;
@@ -56,7 +56,7 @@ int dist_pull(DistMat *dm, double *xloc) {
   if (grid > 2 * c.sms) grid = 2 * c.sms;
   size_t slot_off = (size_t)(xloc - d.heap);
   k_halo_pull<<<grid, kThreads, 0, c.stream>>>(c.state, slot_off, dm->d_owner, dm->d_ridx, dm->nhalo, dm->nl,
-                                              xloc, dm->nbmask, c.tickets);
+                                              xloc, dm->nbmask, c.tickets, gate);
   PSP_LAUNCH_CHECK();
   return PSP_OK;
 }

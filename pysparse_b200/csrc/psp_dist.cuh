@@ -24,6 +24,6 @@ struct DistMat {
 };
 
 DistHost &dist();
-int dist_pull(DistMat *dm, double *xloc);
+int dist_pull(DistMat *dm, double *xloc, int gate = 0);
 
 }  // namespace psp

@@ -50,6 +50,18 @@ static int do_init(int device) {
   PSP_CUDA(cudaEventCreateWithFlags(&c.evpoll[0], cudaEventDisableTiming));
   PSP_CUDA(cudaEventCreateWithFlags(&c.evpoll[1], cudaEventDisableTiming));
   c.ready = true;
+  // PSP_OPTS="name=value,name=value": tuning knobs from the environment (see psp_set_option)
+  if (const char *opts = getenv("PSP_OPTS")) {
+    char buf[256];
+    strncpy(buf, opts, sizeof buf - 1);
+    buf[sizeof buf - 1] = 0;
+    for (char *tok = strtok(buf, ","); tok; tok = strtok(nullptr, ",")) {
+      char *eq = strchr(tok, '=');
+      if (!eq) continue;
+      *eq = 0;
+      psp_set_option(tok, atoll(eq + 1));
+    }
+  }
   return PSP_OK;
 }
 
@@ -225,6 +237,7 @@ extern "C" int psp_set_option(const char *name, long long value) {
   else if (!strcmp(name, "spmv_ctas")) c.spmv_ctas = value;
   else if (!strcmp(name, "poll_chunk")) c.poll_chunk = value;
   else if (!strcmp(name, "use_graph")) c.use_graph = value;
+  else if (!strcmp(name, "l2_stream")) c.l2_stream = value;
   else { set_error("unknown option '%s'", name); return PSP_ERR_ARG; }
   return PSP_OK;
 }

@@ -122,7 +122,7 @@ static int apply_A(Solve &s, const double *dx, double *dy, const double *w1 = nu
   if (s.dm) {
     // dx is a heap vector its producer has published: fetch the halo entries from the
     // neighbours' copies (NVLink), then multiply with the local slab
-    PSP_TRY(dist_pull(s.dm, const_cast<double *>(dx)));
+    PSP_TRY(dist_pull(s.dm, const_cast<double *>(dx), gate));
     SpmvDots d;
     d.w1 = w1; d.w2 = w2; d.w2_is_y = w2_is_y ? 1 : 0; d.epilogue = epilogue; d.S = s.S;
     d.gate = gate;
@@ -486,19 +486,26 @@ struct FBicgUpdate {        // x += alpha phat + omega shat ; r = s - omega t ; 
 
 static int solve_bicgstab(Solve &s, const double *b, double *x, double *work) {
   const long n = s.n;
-  double *r = work, *rhat = work + n, *p = work + 2 * n, *phatb = work + 3 * n, *v = work + 4 * n,
-         *sv = work + 5 * n, *shatb = work + 6 * n, *t = work + 7 * n;
+  const long vs = s.vstride ? s.vstride : n;
+  double *r = work, *rhat = work + vs, *p = work + 2 * vs, *phatb = work + 3 * vs, *v = work + 4 * vs,
+         *sv = work + 5 * vs, *shatb = work + 6 * vs, *t = work + 7 * vs;
   const bool ident = s.fusedK && !s.dinv;
   double *phat = ident ? p : phatb, *shat = ident ? sv : shatb;
+  const int pub = s.dm ? kPublish : 0;     // multi-GPU: phat / shat are read by the neighbours
   PSP_TRY(launch_map(FNormSq{b}, n, EPI_BICG_NORMB));
-  PSP_TRY(apply_A(s, x, r));
+  if (s.dm) {
+    PSP_TRY(launch_map(FCopy{x, t}, n, EPI_NONE, pub));
+    PSP_TRY(apply_A(s, t, r));
+  } else {
+    PSP_TRY(apply_A(s, x, r));
+  }
   PSP_TRY(launch_map(FBicgInit{b, r, rhat, x, 0}, n, EPI_BICG_RES0));
-  const bool sync_each = !(s.A.mat && (s.fusedK || s.K.prec));
+  const bool sync_each = !((s.A.mat || s.dm) && (s.fusedK || s.K.prec));
   auto body = [&](long long) -> int {
-    PSP_TRY(launch_map(FBicgP{r, v, s.fusedK ? s.dinv : nullptr, p, phat, 0, 0, 0}, n));
+    PSP_TRY(launch_map(FBicgP{r, v, s.fusedK ? s.dinv : nullptr, p, phat, 0, 0, 0}, n, EPI_NONE, pub));
     if (!s.fusedK) PSP_TRY(apply_K(s, p, phat));
     PSP_TRY(apply_A(s, phat, v, rhat, nullptr, false, EPI_BICG_ALPHA));
-    PSP_TRY(launch_map(FBicgS{r, v, s.fusedK ? s.dinv : nullptr, sv, shat, 0}, n));
+    PSP_TRY(launch_map(FBicgS{r, v, s.fusedK ? s.dinv : nullptr, sv, shat, 0}, n, EPI_NONE, pub));
     if (!s.fusedK) PSP_TRY(apply_K(s, sv, shat));
     PSP_TRY(apply_A(s, shat, t, sv, nullptr, true, EPI_BICG_OMEGA));
     PSP_TRY(launch_map(FBicgUpdate{phat, shat, sv, t, rhat, x, r, 0, 0}, n, EPI_BICG_RES));
@@ -627,12 +634,22 @@ struct FGmresX {            // x += sum_{j<=last} g[j] W(j)   (gmres.c:177-181) 
 static int solve_gmres(Solve &s, const double *b, double *x, int m) {
   Ctx &c = ctx();
   const long n = s.n;
-  const size_t N = (size_t)n;
-  double *V = nullptr, *W = nullptr, *small = nullptr;
+  const size_t N = (size_t)(s.vstride ? s.vstride : n);     // distance between basis vectors
+  double *V = nullptr, *W = nullptr, *small = nullptr, *xs = nullptr;
   const bool ident = s.fusedK && !s.dinv;
-  auto cleanup = [&]() { cudaFree(V); if (!ident) cudaFree(W); cudaFree(small); };
-  if (cudaMalloc((void **)&V, sizeof(double) * N * (size_t)(m + 1)) != cudaSuccess ||
-      (!ident && cudaMalloc((void **)&W, sizeof(double) * N * (size_t)m) != cudaSuccess) ||
+  const int pub = s.dm ? kPublish : 0;
+  auto cleanup = [&]() { if (!s.dm) { cudaFree(V); if (!ident) cudaFree(W); } cudaFree(small); };
+  if (s.dm) {
+    // multi-GPU: the basis lives in the symmetric heap (every W(i) is multiplied by A)
+    DistHost &d = dist();
+    const int need = (ident ? m + 1 : 2 * m + 1) + 1;
+    if (d.nslots < need) { set_error("gmres: symmetric heap needs %d slots, has %d", need, d.nslots); return PSP_ERR_ARG; }
+    V = d.heap;
+    W = ident ? V : V + (size_t)(m + 1) * N;
+    xs = d.heap + (size_t)(need - 1) * N;
+  }
+  if ((!s.dm && (cudaMalloc((void **)&V, sizeof(double) * N * (size_t)(m + 1)) != cudaSuccess ||
+                 (!ident && cudaMalloc((void **)&W, sizeof(double) * N * (size_t)m) != cudaSuccess))) ||
       cudaMalloc((void **)&small, sizeof(double) * ((size_t)(m + 1) * m + (m + 1) + 2 * (size_t)m)) != cudaSuccess) {
     cudaGetLastError();
     cleanup();
@@ -646,15 +663,19 @@ static int solve_gmres(Solve &s, const double *b, double *x, int m) {
   int st = PSP_OK;
   auto run = [&]() -> int {
     PSP_TRY(launch_map(FNormSq{b}, n, EPI_GMRES_NORMB));
-    const bool sync_each = false;
     auto cycle = [&](long long) -> int {
-      PSP_TRY(apply_A(s, x, V));
+      if (s.dm) {
+        PSP_TRY(launch_map(FCopy{x, xs}, n, EPI_NONE, pub));
+        PSP_TRY(apply_A(s, xs, V));
+      } else {
+        PSP_TRY(apply_A(s, x, V));
+      }
       PSP_TRY(launch_map(FGmresResid{b, V, x, 0}, n, EPI_GMRES_BETA));
-      PSP_TRY(launch_map(FGmresScale{V, G_SCALE0, 0}, n));
+      PSP_TRY(launch_map(FGmresScale{V, G_SCALE0, 0}, n, EPI_NONE, ident ? pub : 0));
       for (int i = 0; i < m; i++) {
         double *vi = V + (size_t)i * N, *vn = V + (size_t)(i + 1) * N, *wi = W + (size_t)i * N;
         if (s.fusedK) {
-          if (s.dinv) PSP_TRY(launch_map(FScaleBy{vi, s.dinv, wi}, n, EPI_NONE, 1));
+          if (s.dinv) PSP_TRY(launch_map(FScaleBy{vi, s.dinv, wi}, n, EPI_NONE, 1 | pub));
         } else {
           if (s.K.prec) PSP_TRY(prec_apply_dev(s.K.prec, vi, wi, s.S));
           else {
@@ -665,7 +686,7 @@ static int solve_gmres(Solve &s, const double *b, double *x, int m) {
             PSP_TRY(apply_callback(s, s.K, vi, wi, false));
           }
         }
-        if (!s.A.mat) {
+        if (!s.A.mat && !s.dm) {
           PSP_CUDA(cudaMemcpyAsync(c.h_state, c.state, sizeof(State), cudaMemcpyDeviceToHost, c.stream));
           PSP_CUDA(cudaStreamSynchronize(c.stream));
           if (c.h_state->done || c.h_state->cyc_done) break;
@@ -676,9 +697,10 @@ static int solve_gmres(Solve &s, const double *b, double *x, int m) {
           const double *vnext = (k < i) ? V + (size_t)(k + 1) * N : nullptr;
           PSP_TRY(launch_map(FGmresMgs{vk, vnext, vn, 0}, n, k < i ? EPI_GMRES_H : EPI_GMRES_HLAST, 1));
         }
-        PSP_TRY(launch_map(FGmresScale{vn, G_INVH, 0}, n, EPI_NONE, 1));
+        // V(i+1) is the next SpMV input when the preconditioner is the identity
+        PSP_TRY(launch_map(FGmresScale{vn, G_INVH, 0}, n, EPI_NONE, 1 | (ident ? pub : 0)));
       }
-      PSP_TRY(launch_map(FGmresX{W, x, G.g, n, 0}, n, EPI_GMRES_CYCLE));
+      PSP_TRY(launch_map(FGmresX{W, x, G.g, (long)N, 0}, n, EPI_GMRES_CYCLE));
       // poll once per restart cycle
       int done = 0;
       PSP_TRY(read_done(s, &done));
@@ -690,7 +712,6 @@ static int solve_gmres(Solve &s, const double *b, double *x, int m) {
       PSP_TRY(cycle(cyc));
       if (c.h_state->done) break;
     }
-    (void)sync_each;
     return PSP_OK;
   };
   st = run();
@@ -793,17 +814,25 @@ int solve_dev(int solver, const psp_operator *Aop, const psp_operator *Kop, int 
 // kernels are the single-GPU ones; reductions are all-reduced in-kernel and
 // the multiplied vector's halo is pulled from the neighbours (psp_dist.cu).
 int dist_solve_dev(int solver, DistMat *dm, psp_prec *K, const double *db, double *dx, double tol,
-                   int maxit, int *info, int *iter, double *relres) {
+                   int maxit, int gmres_dim, int *info, int *iter, double *relres) {
   PSP_TRY(ensure_init());
   Ctx &c = ctx();
   DistHost &d = dist();
   if (!d.ready || !dm) { set_error("psp_dist_solve_dev: distributed layer not initialised"); return PSP_ERR_DIST; }
-  if (solver != PSP_PCG) { set_error("psp_dist_solve_dev: only PCG is sharded in this release"); return PSP_ERR_ARG; }
+  if (solver != PSP_PCG && solver != PSP_BICGSTAB && solver != PSP_GMRES) {
+    set_error("psp_dist_solve_dev: pcg, bicgstab and gmres are sharded in this release");
+    return PSP_ERR_ARG;
+  }
+  if (solver == PSP_GMRES && gmres_dim < 1) { set_error("gmres: dim must be >= 1"); return PSP_ERR_ARG; }
   if (K && !(K->kind == 1 && K->steps == 1 && K->n == dm->nl)) {
     set_error("psp_dist_solve_dev: preconditioner must be None or single-step Jacobi on the local rows");
     return PSP_ERR_ARG;
   }
-  if (d.nslots < 4) { set_error("psp_dist_solve_dev: symmetric heap has fewer than 4 slots"); return PSP_ERR_ARG; }
+  const int need_slots = solver == PSP_PCG ? 4 : (solver == PSP_BICGSTAB ? 8 : 0);
+  if (d.nslots < need_slots) {
+    set_error("psp_dist_solve_dev: symmetric heap has %d slots, the solver needs %d", d.nslots, need_slots);
+    return PSP_ERR_ARG;
+  }
   Solve s;
   s.n = dm->nl;
   s.S = c.state;
@@ -816,13 +845,14 @@ int dist_solve_dev(int solver, DistMat *dm, psp_prec *K, const double *db, doubl
   State init;
   memset(&init, 0, sizeof init);
   init.dist = d.dev;
-  init.maxit = maxit; init.tol = tol; init.iter = -1; init.relres = nan("");
+  init.maxit = maxit; init.tol = tol; init.iter = -1; init.relres = nan(""); init.mdim = gmres_dim;
   c.h_state[0] = init;
   c.h_state[1] = init;
   PSP_CUDA(cudaMemcpyAsync(c.state, &c.h_state[0], sizeof(State), cudaMemcpyHostToDevice, c.stream));
   PSP_CUDA(cudaStreamSynchronize(c.stream));
   PSP_CUDA(cudaEventRecord(c.ev0, c.stream));
-  int st = solve_pcg(s, db, dx, d.heap);
+  int st = solver == PSP_PCG ? solve_pcg(s, db, dx, d.heap)
+         : solver == PSP_BICGSTAB ? solve_bicgstab(s, db, dx, d.heap) : solve_gmres(s, db, dx, gmres_dim);
   if (st != PSP_OK) { cudaStreamSynchronize(c.stream); return st; }
   PSP_CUDA(cudaEventRecord(c.ev1, c.stream));
   PSP_CUDA(cudaMemcpyAsync(&c.h_state[0], c.state, sizeof(State), cudaMemcpyDeviceToHost, c.stream));
@@ -842,8 +872,8 @@ int dist_solve_dev(int solver, DistMat *dm, psp_prec *K, const double *db, doubl
 using namespace psp;
 
 extern "C" int psp_dist_solve_dev(int solver, psp_dmat *A, psp_prec *K, const double *db, double *dx,
-                                  double tol, int maxit, int *info, int *iter, double *relres) {
-  return dist_solve_dev(solver, (DistMat *)A, K, db, dx, tol, maxit, info, iter, relres);
+                                  double tol, int maxit, int gmres_dim, int *info, int *iter, double *relres) {
+  return dist_solve_dev(solver, (DistMat *)A, K, db, dx, tol, maxit, gmres_dim, info, iter, relres);
 }
 
 extern "C" int psp_solve_dev(int solver, const psp_operator *A, const psp_operator *K, int n,

@@ -48,6 +48,7 @@ struct SpmvArgs {
   int w2_is_y;
   int epilogue;
   int gate;
+  int l2_stream;      // TMA loads of the matrix carry an L2 evict-first hint
   State *S;
   double *partials;
   unsigned *ticket;
@@ -193,6 +194,14 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
       "l"(src), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
+__device__ __forceinline__ void tma_load_1d_hint(void *dst, const void *src, uint32_t bytes, uint64_t *bar,
+                                                 uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   asm volatile(
       "{\n"
@@ -230,6 +239,9 @@ __global__ void __launch_bounds__(kThreads) k_spmv_tma(SpmvArgs a) {
   }
   __syncthreads();
 
+  uint64_t l2_policy = 0;
+  if (a.l2_stream) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(l2_policy));
+
   // producer (thread 0): start the bulk copies of row block b into `stage`
   auto issue = [&](int b, int stage) {
     const int2 d0 = __ldg(blk + b), d1 = __ldg(blk + b + 1);
@@ -240,9 +252,18 @@ __global__ void __launch_bounds__(kThreads) k_spmv_tma(SpmvArgs a) {
     const uint32_t nr = (uint32_t)((d1.x + 1 - rbase + 3) & ~3);
     unsigned char *st = smem + (size_t)stage * kStageBytes;
     mbar_expect_tx(&full[stage], ne * 12u + nr * 4u);
-    tma_load_1d(st, a.val + base, ne * 8u, &full[stage]);
-    tma_load_1d(st + kStageVal, a.col + base, ne * 4u, &full[stage]);
-    tma_load_1d(st + kStageVal + kStageCol, a.ind + rbase, nr * 4u, &full[stage]);
+    if (a.l2_stream) {
+      // the matrix is read once per product: mark its lines evict-first so that the
+      // vectors (which ARE re-used, and fit in the 126 MB L2 for sharded / small
+      // problems) are what stays resident
+      tma_load_1d_hint(st, a.val + base, ne * 8u, &full[stage], l2_policy);
+      tma_load_1d_hint(st + kStageVal, a.col + base, ne * 4u, &full[stage], l2_policy);
+      tma_load_1d_hint(st + kStageVal + kStageCol, a.ind + rbase, nr * 4u, &full[stage], l2_policy);
+    } else {
+      tma_load_1d(st, a.val + base, ne * 8u, &full[stage]);
+      tma_load_1d(st + kStageVal, a.col + base, ne * 4u, &full[stage]);
+      tma_load_1d(st + kStageVal + kStageCol, a.ind + rbase, nr * 4u, &full[stage]);
+    }
   };
   if (tid == 0) {
 #pragma unroll
@@ -548,6 +569,7 @@ static int spmv_dispatch(const psp_mat *A, const double *dx, double *dy, const S
   a.x = dx; a.y = dy; a.nb = A->nb;
   a.w1 = d.w1; a.w2 = d.w2; a.w2_is_y = d.w2_is_y; a.epilogue = d.epilogue; a.S = d.S;
   a.gate = d.gate;
+  a.l2_stream = (int)c.l2_stream;
   a.partials = c.partials; a.ticket = c.tickets; a.aux = nullptr;
   if (d.S) a.aux = (void *)(d.S + 1);   // solver-specific small state sits right behind the State
   if (c.spmv_variant == 3 || c.spmv_variant == 0) {

@@ -26,7 +26,7 @@ P.lib.psp_dist_mat_destroy.argtypes = [C.c_void_p]
 P.lib.psp_dist_mat_destroy.restype = None
 P.lib.psp_dist_mat_info.argtypes = [C.c_void_p, _ip, _ip, C.POINTER(C.c_uint)]
 P.lib.psp_dist_solve_dev.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
-                                     C.c_int, _ip, _ip, _dp]
+                                     C.c_int, C.c_int, _ip, _ip, _dp]
 
 HANDLE_BYTES = 128
 
@@ -114,9 +114,15 @@ class ShardedMatrix:
             pass
 
 
-def pcg(A: ShardedMatrix, db: P.DeviceVector, dx: P.DeviceVector, tol: float, maxit: int, K: P.Precon | None = None):
-    """Sharded PCG on device-resident local slices; collective.  Returns (info, iter, relres)."""
+def solve(solver: str, A: ShardedMatrix, db: P.DeviceVector, dx: P.DeviceVector, tol: float, maxit: int,
+          K: P.Precon | None = None, dim: int = 20):
+    """Sharded solve ("pcg", "bicgstab", "gmres") on device-resident local slices; collective.
+    Returns (info, iter, relres)."""
     info, it, rr = C.c_int(), C.c_int(), C.c_double()
-    P.check(P.lib.psp_dist_solve_dev(0, A.ptr, K.ptr if K is not None else None, db.ptr, dx.ptr, tol, maxit,
-                                     C.byref(info), C.byref(it), C.byref(rr)))
+    P.check(P.lib.psp_dist_solve_dev(P.SOLVERS[solver], A.ptr, K.ptr if K is not None else None, db.ptr, dx.ptr,
+                                     tol, maxit, dim, C.byref(info), C.byref(it), C.byref(rr)))
     return info.value, it.value, rr.value
+
+
+def pcg(A, db, dx, tol, maxit, K=None):
+    return solve("pcg", A, db, dx, tol, maxit, K)
