@@ -112,6 +112,7 @@ struct Ctx {
   long long spmv_variant = 0;
   long long spmv_ctas = 0;    // cap on resident CTAs per SM for the TMA SpMV (0: occupancy limit)
   long long l2_stream = 1;    // matrix stream carries an L2 evict-first hint
+  long long pcg_persist = -1; // single-launch PCG: 1 always, 0 never, -1 automatic
   long long poll_chunk = 0;   // 0: automatic
   long long use_graph = 1;
   // sampled SpMV timing (bench.py roofline): event pairs around every Nth launch

@@ -238,6 +238,7 @@ extern "C" int psp_set_option(const char *name, long long value) {
   else if (!strcmp(name, "poll_chunk")) c.poll_chunk = value;
   else if (!strcmp(name, "use_graph")) c.use_graph = value;
   else if (!strcmp(name, "l2_stream")) c.l2_stream = value;
+  else if (!strcmp(name, "pcg_persist")) c.pcg_persist = value;
   else { set_error("unknown option '%s'", name); return PSP_ERR_ARG; }
   return PSP_OK;
 }

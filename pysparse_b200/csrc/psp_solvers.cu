@@ -16,6 +16,8 @@
 namespace psp {
 
 int prec_apply_dev(psp_prec *K, const double *dx, double *dy, State *gateS);   // psp_precon.cu
+int pcg_persist_launch(const psp_mat *M, int n, const double *b, double *x, double *r, double *p, double *q,
+                       const double *dinv, DistMat *dm);                        // psp_persist.cu
 
 // ------------------------------------------------------------------ generic functors
 struct FNormSq {            // red0 = sum a_i^2
@@ -233,6 +235,16 @@ static int solve_pcg(Solve &s, const double *b, double *x, double *work) {
   const long vs = s.vstride ? s.vstride : n;
   double *r = work, *z = work + vs, *p = work + 2 * vs, *q = work + 3 * vs;
   const int pub = s.dm ? kPublish : 0;     // multi-GPU: p is read by the neighbours
+  {
+    // single-launch path: the whole solve in one persistent cooperative kernel
+    // (psp_persist.cu).  pcg_persist: 1 always, 0 never, -1 (default) when the slab is
+    // small enough that launch / barrier latency matters (<= 2^22 rows) or sharded.
+    Ctx &c = ctx();
+    const psp_mat *M = s.dm ? s.dm->local : s.A.mat;
+    const bool eligible = M && s.fusedK;
+    const bool choose = c.pcg_persist == 1 || (c.pcg_persist < 0 && (s.dm || n <= (1L << 22)));
+    if (eligible && choose) return pcg_persist_launch(M, (int)n, b, x, r, p, q, s.dinv, s.dm);
+  }
   PSP_TRY(launch_map(FNormSq{b}, n, EPI_PCG_NORMB));
   if (s.dm) {
     PSP_TRY(launch_map(FCopy{x, p}, n, EPI_NONE, pub));   // x0 into the shared heap, published

@@ -33,10 +33,10 @@
 // y[i]; the lower triangle + diagonal are kept as well for the SSOR sweeps.
 #include "psp_mat.cuh"
 #include "psp_epilogue.cuh"
+#include "psp_tma_ring.cuh"
 
 namespace psp {
 
-constexpr int kBlkNnz = 2044;             // products per row block (+4 slack for alignment)
 constexpr int kProdSlots = kBlkNnz + 4;
 
 struct SpmvArgs {
@@ -54,8 +54,6 @@ struct SpmvArgs {
   unsigned *ticket;
   void *aux;
 };
-
-__device__ __forceinline__ double ldg_f64(const double *p) { return __ldg(p); }
 
 // VEC = 0: scalar 8/4-byte loads;  VEC = 1: aligned 128-bit loads (4 entries / thread / step)
 template <int VEC, bool DOTS>
@@ -177,50 +175,8 @@ __global__ void __launch_bounds__(kThreads, 4) k_spmv_stream(SpmvArgs a) {
 // per row then walks its row in shared memory: consecutive lanes gather
 // x[col] for consecutive rows, which for banded matrices touches 2-3 cache
 // lines per warp instruction instead of one line per diagonal per few lanes.
-__device__ __forceinline__ uint32_t smem_u32(const void *p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-          smem_u32(dst)),
-      "l"(src), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_1d_hint(void *dst, const void *src, uint32_t bytes, uint64_t *bar,
-                                                 uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-          smem_u32(dst)),
-      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
-      : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
-      "}" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-
-constexpr int kStageVal = 2048 * 8;                 // bytes
-constexpr int kStageCol = 2048 * 4;
-constexpr int kStageInd = 272 * 4;                  // kThreads + 1 rows, +3 alignment, rounded to 16 B
-constexpr int kStageBytes = kStageVal + kStageCol + kStageInd;   // 25664, multiple of 128
-
+// The pass itself lives in psp_tma_ring.cuh (shared with the persistent solver
+// kernels).
 template <int STAGES, bool DOTS>
 __global__ void __launch_bounds__(kThreads) k_spmv_tma(SpmvArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -230,133 +186,27 @@ __global__ void __launch_bounds__(kThreads) k_spmv_tma(SpmvArgs a) {
     const volatile State *V = a.S;
     if (V->done || (a.gate == 1 && V->cyc_done)) return;
   }
-  const int tid = threadIdx.x;
-  const int2 *blk = reinterpret_cast<const int2 *>(a.blk);
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < STAGES; s++) mbar_init(&full[s], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
-  uint64_t l2_policy = 0;
-  if (a.l2_stream) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(l2_policy));
-
-  // producer (thread 0): start the bulk copies of row block b into `stage`
-  auto issue = [&](int b, int stage) {
-    const int2 d0 = __ldg(blk + b), d1 = __ldg(blk + b + 1);
-    const int cnt = d1.y - d0.y;
-    if (cnt > kBlkNnz) return;                      // over-long row: read straight from global
-    const int base = d0.y & ~3, rbase = d0.x & ~3;
-    const uint32_t ne = (uint32_t)((d1.y - base + 3) & ~3);
-    const uint32_t nr = (uint32_t)((d1.x + 1 - rbase + 3) & ~3);
-    unsigned char *st = smem + (size_t)stage * kStageBytes;
-    mbar_expect_tx(&full[stage], ne * 12u + nr * 4u);
-    if (a.l2_stream) {
-      // the matrix is read once per product: mark its lines evict-first so that the
-      // vectors (which ARE re-used, and fit in the 126 MB L2 for sharded / small
-      // problems) are what stays resident
-      tma_load_1d_hint(st, a.val + base, ne * 8u, &full[stage], l2_policy);
-      tma_load_1d_hint(st + kStageVal, a.col + base, ne * 4u, &full[stage], l2_policy);
-      tma_load_1d_hint(st + kStageVal + kStageCol, a.ind + rbase, nr * 4u, &full[stage], l2_policy);
-    } else {
-      tma_load_1d(st, a.val + base, ne * 8u, &full[stage]);
-      tma_load_1d(st + kStageVal, a.col + base, ne * 4u, &full[stage]);
-      tma_load_1d(st + kStageVal + kStageCol, a.ind + rbase, nr * 4u, &full[stage]);
-    }
-  };
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < STAGES; s++) {
-      const int b = blockIdx.x + s * gridDim.x;
-      if (b < a.nb) issue(b, s);
-    }
-  }
-
+  MatView A;
+  A.ind = a.ind; A.col = a.col; A.val = a.val; A.nb = a.nb;
+  A.blk = reinterpret_cast<const int2 *>(a.blk);
+  Ring<STAGES> ring;
+  ring.init(smem, full, a.l2_stream != 0);
   double acc0 = 0.0, acc1 = 0.0;
-  int it = 0;
-  uint32_t phases = 0;
-  for (int b = blockIdx.x; b < a.nb; b += gridDim.x, it++) {
-    const int stage = it % STAGES;
-    const uint32_t parity = (phases >> stage) & 1u;   // flips only when the stage was really used
-    const int2 d0 = __ldg(blk + b), d1 = __ldg(blk + b + 1);
-    const int r0 = d0.x, r1 = d1.x, k0 = d0.y, k1 = d1.y;
-    const int nrows = r1 - r0, cnt = k1 - k0;
-    if (cnt <= kBlkNnz) {
-      const unsigned char *st = smem + (size_t)stage * kStageBytes;
-      const double *sval = reinterpret_cast<const double *>(st);
-      const int *scol = reinterpret_cast<const int *>(st + kStageVal);
-      const int *sind = reinterpret_cast<const int *>(st + kStageVal + kStageCol);
-      const int base = k0 & ~3, roff = r0 - (r0 & ~3);
-      mbar_wait(&full[stage], parity);
-      phases ^= (1u << stage);
-      if (cnt <= 16 * nrows) {
-        if (tid < nrows) {
-          const int r = r0 + tid;
-          const int s = sind[roff + tid] - base, e = sind[roff + tid + 1] - base;
-          double sum = 0.0;
-          for (int k = s; k < e; k += 8) {
-            double pr[8];
-#pragma unroll
-            for (int j = 0; j < 8; j++)
-              pr[j] = (k + j < e) ? __dmul_rn(sval[k + j], ldg_f64(a.x + scol[k + j])) : 0.0;
-#pragma unroll
-            for (int j = 0; j < 8; j++)
-              if (k + j < e) sum = __dadd_rn(sum, pr[j]);
-          }
-          a.y[r] = sum;
-          if (DOTS) {
-            if (a.w1) acc0 += a.w1[r] * sum;
-            if (a.w2_is_y) acc1 += sum * sum;
-            else if (a.w2) acc1 += a.w2[r] * sum;
-          }
-        }
-      } else {
-        const int w = tid >> 5, l = tid & 31;
-        for (int rr = w; rr < nrows; rr += kThreads / 32) {
-          const int r = r0 + rr;
-          const int s = sind[roff + rr] - base, e = sind[roff + rr + 1] - base;
-          double sum = 0.0;
-          for (int k = s + l; k < e; k += 32) sum += sval[k] * ldg_f64(a.x + scol[k]);
-          sum = warp_sum(sum);
-          if (l == 0) {
-            a.y[r] = sum;
-            if (DOTS) {
-              if (a.w1) acc0 += a.w1[r] * sum;
-              if (a.w2_is_y) acc1 += sum * sum;
-              else if (a.w2) acc1 += a.w2[r] * sum;
-            }
-          }
-        }
-      }
-    } else {
-      double sum = 0.0;
-      for (int k = k0 + tid; k < k1; k += kThreads)
-        sum += __ldg(a.val + k) * ldg_f64(a.x + __ldg(a.col + k));
-      sum = block_sum(sum, red_sh);
-      if (tid == 0) {
-        a.y[r0] = sum;
-        if (DOTS) {
-          if (a.w1) acc0 += a.w1[r0] * sum;
-          if (a.w2_is_y) acc1 += sum * sum;
-          else if (a.w2) acc1 += a.w2[r0] * sum;
-        }
-      }
+  ring.template pass<true>(A, a.x, red_sh, [&](int r, double sum) {
+    a.y[r] = sum;
+    if (DOTS) {
+      if (a.w1) acc0 += a.w1[r] * sum;
+      if (a.w2_is_y) acc1 += sum * sum;
+      else if (a.w2) acc1 += a.w2[r] * sum;
     }
-    __syncthreads();                                // everyone is done with this stage's buffers
-    if (tid == 0) {
-      const int nb2 = b + STAGES * gridDim.x;
-      if (nb2 < a.nb) issue(nb2, stage);
-    }
-  }
-
+  });
   if (DOTS) {
     double mine[2];
     mine[0] = block_sum(acc0, red_sh);
     mine[1] = block_sum(acc1, red_sh);
     double tot[2], dummy;
     if (grid_reduce_finish<2, false>(mine, 0.0, a.partials, a.ticket, tot, &dummy, red_sh, a.S->dist)) {
-      if (tid == 0) {
+      if (threadIdx.x == 0) {
         a.S->red[0] = tot[0];
         a.S->red[1] = tot[1];
         run_epilogue(a.epilogue, a.S, a.aux);
