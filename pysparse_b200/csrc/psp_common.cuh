@@ -111,7 +111,7 @@ struct Ctx {
   // options
   long long spmv_variant = 0;
   long long spmv_ctas = 0;    // cap on resident CTAs per SM for the TMA SpMV (0: occupancy limit)
-  long long l2_stream = 1;    // matrix stream carries an L2 evict-first hint
+  long long l2_stream = -1;   // L2 evict-first hint on the matrix stream: 1 on, 0 off, -1 automatic
   long long pcg_persist = -1; // single-launch PCG: 1 always, 0 never, -1 automatic
   long long poll_chunk = 0;   // 0: automatic
   long long use_graph = 1;
@@ -127,6 +127,15 @@ struct Ctx {
 Ctx &ctx();
 int ensure_init();                   // PSP_OK or error; lazily initialises device 0
 int ensure_stage(size_t elems);      // pinned staging buffer of at least `elems` doubles
+
+// The matrix is streamed once per product, the vectors are re-used: when the vectors of
+// the problem (<= 3 M rows: 6 vectors <= 144 MB) can live in the 126 MB L2, the TMA loads
+// of the matrix carry an evict-first hint so that they do not push the vectors out.
+inline int l2_stream_for(long rows) {
+  Ctx &c = ctx();
+  if (c.l2_stream >= 0) return c.l2_stream ? 1 : 0;
+  return rows <= 3L * 1000 * 1000 ? 1 : 0;
+}
 
 inline int grid_for(size_t work_items, int per_sm = 8) {
   Ctx &c = ctx();

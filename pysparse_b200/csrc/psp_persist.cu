@@ -291,7 +291,7 @@ int pcg_persist_launch(const psp_mat *M, int n, const double *b, double *x, doub
   a.A.ind = M->d_ind; a.A.col = M->d_col; a.A.val = M->d_val; a.A.nb = M->nb;
   a.A.blk = reinterpret_cast<const int2 *>(M->d_blk);
   a.n = n; a.b = b; a.x = x; a.r = r; a.p = p; a.q = q; a.dinv = dinv;
-  a.S = c.state; a.partials = g_partials2; a.l2_stream = (int)c.l2_stream;
+  a.S = c.state; a.partials = g_partials2; a.l2_stream = l2_stream_for(n);
   a.halo_owner = dm ? dm->d_owner : nullptr; a.halo_ridx = dm ? dm->d_ridx : nullptr;
   a.nhalo = dm ? dm->nhalo : 0; a.nbmask = dm ? dm->nbmask : 0u;
   size_t p_slot_off = dm ? (size_t)(p - dist().heap) : 0;

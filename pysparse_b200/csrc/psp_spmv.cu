@@ -419,7 +419,7 @@ static int spmv_dispatch(const psp_mat *A, const double *dx, double *dy, const S
   a.x = dx; a.y = dy; a.nb = A->nb;
   a.w1 = d.w1; a.w2 = d.w2; a.w2_is_y = d.w2_is_y; a.epilogue = d.epilogue; a.S = d.S;
   a.gate = d.gate;
-  a.l2_stream = (int)c.l2_stream;
+  a.l2_stream = l2_stream_for(A->m);
   a.partials = c.partials; a.ticket = c.tickets; a.aux = nullptr;
   if (d.S) a.aux = (void *)(d.S + 1);   // solver-specific small state sits right behind the State
   if (c.spmv_variant == 3 || c.spmv_variant == 0) {

@@ -85,6 +85,14 @@ def run(args, bench):
     launches = P.launch_count()
     n_spmv, spmv_ms = P.spmv_timing(0)
     clk = clocks.stop() if rank == 0 else None
+    if n_spmv == 0:
+        # the sharded solve ran as ONE persistent kernel (no separate SpMV launches to
+        # sample): time the SpMV kernel in one extra solve on the per-phase path
+        P.set_option("pcg_persist", 0)
+        P.spmv_timing(4)
+        step()
+        n_spmv, spmv_ms = P.spmv_timing(0)
+        P.set_option("pcg_persist", -1)
 
     # max over ranks of the device-timed region
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")

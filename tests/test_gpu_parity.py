@@ -175,9 +175,16 @@ def test_device_resident_solve_and_launch_counter(native):
     S = native.Matrix.sss(n, *mat["sss"])
     K = native.Precon.jacobi(S, mat["sss"][1])
     db = native.DeviceVector(n, np.ones(n)); dx = native.DeviceVector(n, np.zeros(n))
+    native.set_option("pcg_persist", 0)          # per-phase kernels: >= 3 launches per iteration
     native.launch_count(reset=True)
     r = native.solve("pcg", S, db, dx, 1e-10, 1000, K, dev=True)
     assert r[0] == 0 and native.launch_count() >= 3 * r[1]
+    native.set_option("pcg_persist", 1)          # single-launch persistent kernel: same result
+    dx.fill(0.0)
+    native.launch_count(reset=True)
+    r1 = native.solve("pcg", S, db, dx, 1e-10, 1000, K, dev=True)
+    native.set_option("pcg_persist", -1)
+    assert native.launch_count() == 2 and r1[:2] == r[:2] and abs(r1[2] - r[2]) <= 1e-12
     x = dx.download()
     y = np.zeros(n); S.matvec(x, y)
     assert np.linalg.norm(1.0 - y) / np.sqrt(n) <= 1e-9
