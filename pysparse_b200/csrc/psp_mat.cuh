@@ -41,9 +41,15 @@ struct psp_prec {
   int nlev_f = 0, nlev_b = 0;
   int *d_rows_f = nullptr, *d_lptr_f = nullptr;   // rows sorted by forward level, level pointers
   int *d_rows_b = nullptr, *d_lptr_b = nullptr;
-  // L^T in CSR with entries of each row in DESCENDING original-row order
-  int *d_tind = nullptr, *d_tcol = nullptr;
-  double *d_tval = nullptr;
+  // level-major copies of the sweep operands: position p of the forward (backward)
+  // schedule is row rows_f[p] (rows_b[p]); its entries are f_col/f_val[f_ind[p]..f_ind[p+1])
+  // = row of L in ascending column order (b_*: row of L^T in DESCENDING original-row
+  // order, the order the reference's backward loop scatters in).  Column indices
+  // stay in the original numbering (vectors are not permuted).
+  int *d_find = nullptr, *d_fcol = nullptr, *d_bind = nullptr, *d_bcol = nullptr;
+  int *d_floc = nullptr, *d_bloc = nullptr;       // per entry: position in the previous level, or -1
+  double *d_fval = nullptr, *d_bval = nullptr;
+  int maxw_f = 0, maxw_b = 0;                     // widest level of each schedule
   std::vector<int> h_level_f, h_level_b;
   unsigned *d_bar = nullptr;                      // grid barrier counter
   double *d_x = nullptr, *d_y = nullptr;

@@ -7,12 +7,20 @@
 // (psp_ssor_create) computes, on the host, the level sets of the dependency
 // graph of L (forward sweep: row i needs x[j] for every stored L[i,j], j < i)
 // and of L^T (backward sweep: row i needs x[i'] for every stored L[i',i],
-// i' > i), plus a transpose index of L whose rows list their entries by
-// DESCENDING original row -- the order in which the reference's backward loop
-// scatters into y[j] -- so the scatter becomes an atomic-free gather with the
-// same accumulation order.  Rows inside one level are independent; a single
-// persistent cooperative kernel walks the levels with a grid-wide barrier in
-// between, so one preconditioner application is ONE launch.
+// i' > i), and builds LEVEL-MAJOR copies of the operands: the rows of a level
+// are stored back to back (coalesced streaming), forward rows list their
+// entries in ascending column order, backward rows in DESCENDING original-row
+// order -- the order in which the reference's backward loop scatters into
+// y[j] -- so the scatter becomes an atomic-free gather with the same
+// accumulation order and the results are bit-identical to the reference.
+//
+// Rows inside a level are independent; levels are separated by a barrier.
+// Two engines, one launch per preconditioner application either way:
+//   * narrow levels (lexicographic 2-D grids: 2n-1 levels of <= n rows): ONE
+//     thread-block cluster; the per-level barrier is the hardware cluster
+//     barrier (barrier.cluster arrive/wait, ~0.2 us) and the next level's row
+//     data is prefetched between arrive and wait;
+//   * wide levels: persistent cooperative grid with grid.sync() per level.
 #include <cooperative_groups.h>
 #include "psp_mat.cuh"
 #include "psp_vec.cuh"
@@ -36,12 +44,9 @@ struct FJacobiScale {       // y = x .* dinv                   (preconmodule.c:4
 
 struct SweepArgs {
   int n;
-  const int *lind, *lcol;       // L rows (ascending columns)
-  const double *lval, *diag;
-  const int *tind, *tcol;       // L^T rows, entries by descending original row
-  const double *tval;
-  const int *rows_f, *lptr_f; int nlev_f;
-  const int *rows_b, *lptr_b; int nlev_b;
+  const double *diag;
+  const int *rows_f, *lptr_f, *find, *fcol; const double *fval; int nlev_f;
+  const int *rows_b, *lptr_b, *bind, *bcol; const double *bval; int nlev_b;
   const double *b;              // right-hand side (the vector being preconditioned)
   double *x;                    // result
   double *w;                    // work: L x / L^T x   (reference: y resp. h)
@@ -50,91 +55,299 @@ struct SweepArgs {
   const State *S;               // optional gate
 };
 
-// symmetric Gauss-Seidel, omega == 1  (symgs_kernel, preconmodule.c:149-193)
-__global__ void __launch_bounds__(kThreads) k_symgs(SweepArgs a) {
+// One row of a sweep.  RELAX = false: symgs_kernel (preconmodule.c:149-193);
+// RELAX = true: ssor_kernel (:95-143).  fwd selects the half-step.  The
+// expression order is the reference's, every operation rounded separately.
+template <bool RELAX>
+__device__ __forceinline__ void sweep_row(const SweepArgs &a, bool fwd, int step, int r, int k0, int k1,
+                                          const int *col, const double *val) {
+  const double d = a.diag[r], br = a.b[r];
+  if (!RELAX) {
+    double s = 0.0;
+    for (int k = k0; k < k1; k++) s = __dadd_rn(s, __dmul_rn(val[k], __ldcg(a.x + col[k])));
+    // forward: x_i = (b_i - w_i - s)/d_i, w_i = s  (w = 0 in the first step)
+    // backward: x_i = (b_i - (Lx)_i - t)/d_i, w_i = t  with (Lx)_i left in w by the forward sweep
+    const double wr = (fwd && step == 0) ? 0.0 : a.w[r];
+    a.x[r] = __ddiv_rn(__dsub_rn(__dsub_rn(br, wr), s), d);
+    a.w[r] = s;
+  } else {
+    const double om = a.omega, om1 = 1.0 - a.omega;
+    double temp;
+    if (fwd && step == 0) temp = __dmul_rn(om, br);
+    else temp = __dadd_rn(__dadd_rn(__dmul_rn(__dmul_rn(om1, a.x[r]), d), a.w[r]), __dmul_rn(om, br));
+    double s = 0.0;
+    for (int k = k0; k < k1; k++) s = __dsub_rn(s, __dmul_rn(val[k], __ldcg(a.x + col[k])));
+    const double h = __dmul_rn(om, s);
+    a.w[r] = h;
+    a.x[r] = __ddiv_rn(__dadd_rn(temp, h), d);
+  }
+}
+
+// ---------------------------------------------------------------- grid-wide engine
+template <bool RELAX>
+__global__ void __launch_bounds__(kThreads) k_sweep_grid(SweepArgs a) {
   if (a.S && *(const volatile int *)&a.S->done) return;
   cg::grid_group grid = cg::this_grid();
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
   const int gsz = gridDim.x * blockDim.x;
   for (int step = 0; step < a.steps; step++) {
-    // forward: x_i = (b_i - w_i - s)/d_i ; w_i = s = sum_{j<i} L_ij x_j
-    for (int l = 0; l < a.nlev_f; l++) {
-      const int p0 = a.lptr_f[l], p1 = a.lptr_f[l + 1];
-      for (int p = p0 + gtid; p < p1; p += gsz) {
-        const int r = a.rows_f[p];
-        double s = 0.0;
-        for (int k = a.lind[r]; k < a.lind[r + 1]; k++)
-          s = __dadd_rn(s, __dmul_rn(a.lval[k], __ldcg(a.x + a.lcol[k])));
-        const double wr = (step == 0) ? 0.0 : a.w[r];
-        a.x[r] = __ddiv_rn(__dsub_rn(__dsub_rn(a.b[r], wr), s), a.diag[r]);
-        a.w[r] = s;
+    for (int half = 0; half < 2; half++) {
+      const bool fwd = (half == 0);
+      const int nlev = fwd ? a.nlev_f : a.nlev_b;
+      const int *lptr = fwd ? a.lptr_f : a.lptr_b, *rows = fwd ? a.rows_f : a.rows_b;
+      const int *ind = fwd ? a.find : a.bind, *col = fwd ? a.fcol : a.bcol;
+      const double *val = fwd ? a.fval : a.bval;
+      for (int l = 0; l < nlev; l++) {
+        const int p0 = lptr[l], p1 = lptr[l + 1];
+        for (int p = p0 + gtid; p < p1; p += gsz) sweep_row<RELAX>(a, fwd, step, rows[p], ind[p], ind[p + 1], col, val);
+        grid.sync();
       }
-      grid.sync();
-    }
-    // backward: t = sum_{i'>i} L_i'i x_i' (descending i') ; x_i = (b_i - (Lx)_i - t)/d_i ; w_i = t
-    for (int l = 0; l < a.nlev_b; l++) {
-      const int p0 = a.lptr_b[l], p1 = a.lptr_b[l + 1];
-      for (int p = p0 + gtid; p < p1; p += gsz) {
-        const int r = a.rows_b[p];
-        double t = 0.0;
-        for (int k = a.tind[r]; k < a.tind[r + 1]; k++)
-          t = __dadd_rn(t, __dmul_rn(a.tval[k], __ldcg(a.x + a.tcol[k])));
-        const double s = a.w[r];
-        a.x[r] = __ddiv_rn(__dsub_rn(__dsub_rn(a.b[r], s), t), a.diag[r]);
-        a.w[r] = t;
-      }
-      grid.sync();
     }
   }
 }
 
-// SSOR with relaxation, omega != 1  (ssor_kernel, preconmodule.c:95-143)
-__global__ void __launch_bounds__(kThreads) k_ssor(SweepArgs a) {
+// ---------------------------------------------------------------- cluster engine
+constexpr int kSweepThreads = 512;
+
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+// Per-thread software pipeline in shared memory (cp.async / LDGSTS): every thread owns
+// private ring slots, so no CTA-level synchronisation is involved.  While level l is
+// being computed, the row METADATA (row index, entry range) of level l+4 and the row
+// DATA (diagonal, right-hand side, work value, first kPre entries) of level l+2 are in
+// flight: after the cluster barrier only the x gathers (L2 hits: written one level ago)
+// and ~10 dependent flops remain on the critical path.
+constexpr int kPre = 4;         // entries per row prefetched into shared memory
+constexpr int kMetaRing = 5;
+constexpr int kDataRing = 3;
+constexpr int kLptrChunk = 8192;
+
+__device__ __forceinline__ void cp_async4(void *dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr size_t kSweepSmem = sizeof(int) * (kLptrChunk + 8 + 3 * kMetaRing * kSweepThreads + kDataRing * kPre * kSweepThreads) +
+                              sizeof(double) * (4 * kDataRing * kSweepThreads + kDataRing * kPre * kSweepThreads);
+
+template <bool RELAX>
+__global__ void __launch_bounds__(kSweepThreads, 1) k_sweep_cluster(SweepArgs a) {
   if (a.S && *(const volatile int *)&a.S->done) return;
-  cg::grid_group grid = cg::this_grid();
-  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int gsz = gridDim.x * blockDim.x;
-  const double om = a.omega, om1 = 1.0 - a.omega;
+  extern __shared__ __align__(16) unsigned char sweep_smem[];
+  constexpr int T = kSweepThreads;
+  double *s_d = reinterpret_cast<double *>(sweep_smem);          // [kDataRing][T]
+  double *s_b = s_d + kDataRing * T;
+  double *s_w = s_b + kDataRing * T;
+  double *s_xo = s_w + kDataRing * T;
+  double *s_v = s_xo + kDataRing * T;                             // [kDataRing][kPre][T]
+  int *s_c = reinterpret_cast<int *>(s_v + kDataRing * kPre * T); // [kDataRing][kPre][T]
+  int *s_r = s_c + kDataRing * kPre * T;                          // [kMetaRing][T]
+  int *s_k0 = s_r + kMetaRing * T;
+  int *s_k1 = s_k0 + kMetaRing * T;
+  int *s_lptr = s_k1 + kMetaRing * T;                             // [kLptrChunk + 8]
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const int tid = threadIdx.x;
+  const int ctid = (int)cluster.block_rank() * T + tid;
+  const int csz = (int)cluster.num_blocks() * T;
+
   for (int step = 0; step < a.steps; step++) {
-    for (int l = 0; l < a.nlev_f; l++) {
-      const int p0 = a.lptr_f[l], p1 = a.lptr_f[l + 1];
-      for (int p = p0 + gtid; p < p1; p += gsz) {
-        const int r = a.rows_f[p];
-        const double d = a.diag[r], br = a.b[r];
-        double temp;
-        if (step == 0) temp = __dmul_rn(om, br);
-        else temp = __dadd_rn(__dadd_rn(__dmul_rn(__dmul_rn(om1, a.x[r]), d), a.w[r]), __dmul_rn(om, br));
-        double s = 0.0;
-        for (int k = a.lind[r]; k < a.lind[r + 1]; k++)
-          s = __dsub_rn(s, __dmul_rn(a.lval[k], __ldcg(a.x + a.lcol[k])));
-        const double h = __dmul_rn(om, s);
-        a.w[r] = h;
-        a.x[r] = __ddiv_rn(__dadd_rn(temp, h), d);
+    for (int half = 0; half < 2; half++) {
+      const bool fwd = (half == 0);
+      const int nlev = fwd ? a.nlev_f : a.nlev_b;
+      const int *lptr = fwd ? a.lptr_f : a.lptr_b, *rows = fwd ? a.rows_f : a.rows_b;
+      const int *ind = fwd ? a.find : a.bind, *col = fwd ? a.fcol : a.bcol;
+      const double *val = fwd ? a.fval : a.bval;
+      const bool need_w = RELAX ? !(fwd && step == 0) : !(fwd && step == 0);
+      const bool need_xo = RELAX && !(fwd && step == 0);
+
+      for (int base = 0; base < nlev; base += kLptrChunk) {
+        const int nl = (nlev - base < kLptrChunk) ? nlev - base : kLptrChunk;   // levels in this chunk
+        __syncthreads();
+        for (int i = tid; i <= nl; i += T) s_lptr[i] = __ldg(lptr + base + i);
+        __syncthreads();
+
+        auto issue_meta = [&](int L) {        // L relative to the chunk
+          if (L < nl) {
+            const int p = s_lptr[L] + ctid, slot = (L % kMetaRing) * T + tid;
+            if (p < s_lptr[L + 1]) {
+              cp_async4(&s_r[slot], rows + p);
+              cp_async4(&s_k0[slot], ind + p);
+              cp_async4(&s_k1[slot], ind + p + 1);
+            } else {
+              s_r[slot] = -1;
+            }
+          }
+          cp_commit();
+        };
+        auto issue_data = [&](int L) {        // the metadata of level L has landed
+          if (L >= 0 && L < nl) {
+            const int ms = (L % kMetaRing) * T + tid, ds = (L % kDataRing) * T + tid;
+            const int r = s_r[ms];
+            if (r >= 0) {
+              const int k0 = s_k0[ms], k1 = s_k1[ms];
+              cp_async8(&s_d[ds], a.diag + r);
+              cp_async8(&s_b[ds], a.b + r);
+              if (need_w) cp_async8(&s_w[ds], a.w + r);
+              if (need_xo) cp_async8(&s_xo[ds], a.x + r);
+#pragma unroll
+              for (int j = 0; j < kPre; j++)
+                if (k0 + j < k1) {
+                  const int es = ((L % kDataRing) * kPre + j) * T + tid;
+                  cp_async4(&s_c[es], col + k0 + j);
+                  cp_async8(&s_v[es], val + k0 + j);
+                }
+            }
+          }
+          cp_commit();
+        };
+
+        // (A variant that issues untracked prefetch.global.L2 hints far ahead and copies
+        // L2-resident data at the start of each iteration measured slower on B200:
+        // 4.4 vs 3.55 us per level, profiles/r1_ssor_notes.md.)
+        for (int l = -4; l < nl; l++) {
+          if (l >= 0) {
+            cp_wait<2>();                     // data of level l is in shared memory
+            const int ms = (l % kMetaRing) * T + tid, ds = (l % kDataRing) * T + tid;
+            const int r = s_r[ms];
+            if (r >= 0) {
+              const int k0 = s_k0[ms], k1 = s_k1[ms];
+              const double d = s_d[ds], br = s_b[ds];
+              double s = 0.0;
+#pragma unroll
+              for (int j = 0; j < kPre; j++)
+                if (k0 + j < k1) {
+                  const int es = ((l % kDataRing) * kPre + j) * T + tid;
+                  const double pr = __dmul_rn(s_v[es], __ldcg(a.x + s_c[es]));
+                  s = RELAX ? __dsub_rn(s, pr) : __dadd_rn(s, pr);
+                }
+              for (int k = k0 + kPre; k < k1; k++) {
+                const double pr = __dmul_rn(__ldg(val + k), __ldcg(a.x + __ldg(col + k)));
+                s = RELAX ? __dsub_rn(s, pr) : __dadd_rn(s, pr);
+              }
+              if (!RELAX) {
+                const double wr = need_w ? s_w[ds] : 0.0;
+                a.x[r] = __ddiv_rn(__dsub_rn(__dsub_rn(br, wr), s), d);
+                a.w[r] = s;
+              } else {
+                const double om = a.omega, om1 = 1.0 - a.omega;
+                double temp;
+                if (!need_xo) temp = __dmul_rn(om, br);
+                else temp = __dadd_rn(__dadd_rn(__dmul_rn(__dmul_rn(om1, s_xo[ds]), d), s_w[ds]), __dmul_rn(om, br));
+                const double h = __dmul_rn(om, s);
+                a.w[r] = h;
+                a.x[r] = __ddiv_rn(__dadd_rn(temp, h), d);
+              }
+            }
+            // levels wider than the cluster: remaining rows straight from global memory
+            for (int pp = s_lptr[l] + ctid + csz; pp < s_lptr[l + 1]; pp += csz)
+              sweep_row<RELAX>(a, fwd, step, __ldg(rows + pp), __ldg(ind + pp), __ldg(ind + pp + 1), col, val);
+            cluster_arrive();
+          }
+          issue_meta(l + 4);
+          cp_wait<4>();                       // metadata of level l+2 has landed
+          issue_data(l + 2);
+          if (l >= 0) cluster_wait();
+        }
+        cp_wait<0>();
       }
-      grid.sync();
-    }
-    for (int l = 0; l < a.nlev_b; l++) {
-      const int p0 = a.lptr_b[l], p1 = a.lptr_b[l + 1];
-      for (int p = p0 + gtid; p < p1; p += gsz) {
-        const int r = a.rows_b[p];
-        const double d = a.diag[r];
-        const double temp = __dadd_rn(__dadd_rn(__dmul_rn(__dmul_rn(om1, a.x[r]), d), a.w[r]),
-                                      __dmul_rn(om, a.b[r]));
-        double t = 0.0;
-        for (int k = a.tind[r]; k < a.tind[r + 1]; k++)
-          t = __dsub_rn(t, __dmul_rn(a.tval[k], __ldcg(a.x + a.tcol[k])));
-        const double h = __dmul_rn(om, t);
-        a.w[r] = h;
-        a.x[r] = __ddiv_rn(__dadd_rn(temp, h), d);
-      }
-      grid.sync();
     }
   }
 }
 
-static int sweep_grid(const void *kernel) {
-  static int cached_symgs = 0, cached_ssor = 0;
-  int *slot = (kernel == (const void *)k_symgs) ? &cached_symgs : &cached_ssor;
+// ---------------------------------------------------------------- single-CTA engine
+// For long chains of narrow levels the cheapest barrier by far is bar.sync
+// (measured on B200: 0.02 us vs 0.24 us for an empty cluster barrier and ~0.85 us once
+// a global store has to be released to another SM).  One CTA walks all levels; a row
+// reads the x values produced in the PREVIOUS level from shared memory (loc[k] >= 0 is
+// the position of column k inside that level) and older ones from global memory (same
+// SM, ordered by the barrier).  DRAM latency is taken off the critical path with L2
+// prefetch hints issued a few levels ahead.
+constexpr int kCtaThreads = 1024;
+constexpr int kCtaRows = 8;          // rows per thread and level that get scattered-vector hints
+
+template <bool RELAX>
+__global__ void __launch_bounds__(kCtaThreads, 1) k_sweep_cta(SweepArgs a, const int *floc, const int *bloc, int maxw) {
+  if (a.S && *(const volatile int *)&a.S->done) return;
+  extern __shared__ double xs[];      // [2][maxw]
+  constexpr int T = kCtaThreads;
+  const int tid = threadIdx.x;
+  for (int step = 0; step < a.steps; step++) {
+    for (int half = 0; half < 2; half++) {
+      const bool fwd = (half == 0);
+      const int nlev = fwd ? a.nlev_f : a.nlev_b;
+      const int *lptr = fwd ? a.lptr_f : a.lptr_b, *rows = fwd ? a.rows_f : a.rows_b;
+      const int *ind = fwd ? a.find : a.bind, *col = fwd ? a.fcol : a.bcol, *loc = fwd ? floc : bloc;
+      const double *val = fwd ? a.fval : a.bval;
+      const bool need_w = !(fwd && step == 0);
+      for (int l = 0; l < nlev; l++) {
+        const int p0 = __ldg(lptr + l), p1 = __ldg(lptr + l + 1);
+        double *cur = xs + (size_t)(l & 1) * maxw;
+        const double *prev = xs + (size_t)((l & 1) ^ 1) * maxw;
+        // rows of level l+2 whose scattered vector entries get an L2 hint below (loaded
+        // now so that the latency overlaps the compute)
+        int hr[kCtaRows];
+        {
+          const int q0 = (l + 2 < nlev) ? __ldg(lptr + l + 2) : 0, q1 = (l + 2 < nlev) ? __ldg(lptr + l + 3) : 0;
+#pragma unroll
+          for (int j = 0; j < kCtaRows; j++) { const int q = q0 + tid + j * T; hr[j] = (q < q1) ? __ldg(rows + q) : -1; }
+        }
+        for (int p = p0 + tid; p < p1; p += T) {
+          const int r = __ldg(rows + p), k0 = __ldg(ind + p), k1 = __ldg(ind + p + 1);
+          const double d = __ldg(a.diag + r), br = __ldg(a.b + r);
+          double s = 0.0;
+          for (int k = k0; k < k1; k++) {
+            const int lc = __ldg(loc + k);
+            const double xv = (lc >= 0) ? prev[lc] : a.x[__ldg(col + k)];
+            const double pr = __dmul_rn(__ldg(val + k), xv);
+            s = RELAX ? __dsub_rn(s, pr) : __dadd_rn(s, pr);
+          }
+          double xn;
+          if (!RELAX) {
+            const double wr = need_w ? a.w[r] : 0.0;
+            xn = __ddiv_rn(__dsub_rn(__dsub_rn(br, wr), s), d);
+            a.w[r] = s;
+          } else {
+            const double om = a.omega, om1 = 1.0 - a.omega;
+            double temp;
+            if (!need_w) temp = __dmul_rn(om, br);
+            else temp = __dadd_rn(__dadd_rn(__dmul_rn(__dmul_rn(om1, a.x[r]), d), a.w[r]), __dmul_rn(om, br));
+            const double h = __dmul_rn(om, s);
+            a.w[r] = h;
+            xn = __ddiv_rn(__dadd_rn(temp, h), d);
+          }
+          a.x[r] = xn;
+          cur[p - p0] = xn;
+        }
+        // L2 hints: scattered vector entries of level l+2, streamed arrays of level l+4
+#pragma unroll
+        for (int j = 0; j < kCtaRows; j++)
+          if (hr[j] >= 0) {
+            prefetch_l2(a.diag + hr[j]); prefetch_l2(a.b + hr[j]);
+            if (need_w) prefetch_l2(a.w + hr[j]);
+          }
+        if (l + 4 < nlev) {
+          const int q0 = __ldg(lptr + l + 4), q1 = __ldg(lptr + l + 5);
+          for (int q = q0 + tid * 32; q < q1; q += T * 32) { prefetch_l2(rows + q); prefetch_l2(ind + q); }
+          const int e0 = __ldg(ind + q0), e1 = __ldg(ind + q1);
+          for (int e = e0 + tid * 16; e < e1; e += T * 16) { prefetch_l2(col + e); prefetch_l2(loc + e); prefetch_l2(val + e); }
+        }
+        __syncthreads();
+      }
+    }
+  }
+}
+
+static int grid_engine_blocks(const void *kernel) {
+  static int cached[2] = {0, 0};
+  int *slot = (kernel == (const void *)k_sweep_grid<false>) ? &cached[0] : &cached[1];
   if (*slot == 0) {
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0) != cudaSuccess || per_sm < 1)
@@ -159,17 +372,64 @@ int prec_apply_dev(psp_prec *K, const double *dx, double *dy, State *gateS) {
     }
     return PSP_OK;
   }
-  const psp_mat *A = K->mat;
   SweepArgs a;
   a.n = (int)n;
-  a.lind = A->d_lind; a.lcol = A->d_lcol; a.lval = A->d_lval; a.diag = A->d_diag;
-  a.tind = K->d_tind; a.tcol = K->d_tcol; a.tval = K->d_tval;
-  a.rows_f = K->d_rows_f; a.lptr_f = K->d_lptr_f; a.nlev_f = K->nlev_f;
-  a.rows_b = K->d_rows_b; a.lptr_b = K->d_lptr_b; a.nlev_b = K->nlev_b;
+  a.diag = K->mat->d_diag;
+  a.rows_f = K->d_rows_f; a.lptr_f = K->d_lptr_f; a.find = K->d_find; a.fcol = K->d_fcol; a.fval = K->d_fval;
+  a.nlev_f = K->nlev_f;
+  a.rows_b = K->d_rows_b; a.lptr_b = K->d_lptr_b; a.bind = K->d_bind; a.bcol = K->d_bcol; a.bval = K->d_bval;
+  a.nlev_b = K->nlev_b;
   a.b = dx; a.x = dy; a.w = K->d_t1; a.omega = K->omega; a.steps = K->steps; a.S = gateS;
-  const void *kern = (K->omega == 1.0) ? (const void *)k_symgs : (const void *)k_ssor;
+  const bool relax = (K->omega != 1.0);
+  // engine choice: many narrow levels -> one cluster with the hardware barrier; few wide
+  // levels -> the whole GPU with grid.sync.  ssor_engine: 0 auto, 1 grid, 2 cluster.
+  const int maxw = K->maxw_f > K->maxw_b ? K->maxw_f : K->maxw_b;
+  const long nlev = (long)K->nlev_f + K->nlev_b;
+  bool use_cluster = (maxw <= 4 * c.ssor_cluster * kSweepThreads) && nlev >= 64;
+  if (c.ssor_engine == 1) use_cluster = false;
+  if (c.ssor_engine == 2) use_cluster = true;
+  // single CTA: chains of narrow levels (lexicographic 2-D grids); needs 2 x maxw doubles of smem
+  // (experimental, never chosen automatically: one SM cannot stream the operands fast
+  // enough -- 9.8 us per level at 4096^2 vs 3.6 for the cluster engine)
+  const bool use_cta = (c.ssor_engine == 3) && maxw <= 12288;
+  if (use_cta) {
+    const void *kern = relax ? (const void *)k_sweep_cta<true> : (const void *)k_sweep_cta<false>;
+    const size_t smem = sizeof(double) * 2 * (size_t)(maxw > 0 ? maxw : 1);
+    static size_t prepared_smem[2] = {0, 0};
+    if (prepared_smem[relax ? 1 : 0] < smem) {
+      PSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      prepared_smem[relax ? 1 : 0] = smem;
+    }
+    int mw = maxw;
+    const int *fl = K->d_floc, *bl = K->d_bloc;
+    void *args[] = {&a, &fl, &bl, &mw};
+    PSP_CUDA(cudaLaunchKernel(kern, dim3(1), dim3(kCtaThreads), args, smem, c.stream));
+    c.launches++;
+    return PSP_OK;
+  }
+  if (use_cluster) {
+    const void *kern = relax ? (const void *)k_sweep_cluster<true> : (const void *)k_sweep_cluster<false>;
+    int csize = (int)c.ssor_cluster;
+    static bool prepared[2] = {false, false};
+    if (!prepared[relax ? 1 : 0]) {
+      PSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSweepSmem));
+      PSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      prepared[relax ? 1 : 0] = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(csize); cfg.blockDim = dim3(kSweepThreads); cfg.dynamicSmemBytes = kSweepSmem; cfg.stream = c.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    void *args[] = {&a};
+    PSP_CUDA(cudaLaunchKernelExC(&cfg, kern, args));
+    c.launches++;
+    return PSP_OK;
+  }
+  const void *kern = relax ? (const void *)k_sweep_grid<true> : (const void *)k_sweep_grid<false>;
   void *args[] = {&a};
-  PSP_CUDA(cudaLaunchCooperativeKernel(kern, dim3(sweep_grid(kern)), dim3(kThreads), args, 0, c.stream));
+  PSP_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid_engine_blocks(kern)), dim3(kThreads), args, 0, c.stream));
   c.launches++;
   return PSP_OK;
 }
@@ -180,16 +440,51 @@ static int upload_i(const std::vector<int> &v, int **d) {
   if (!v.empty()) PSP_CUDA(cudaMemcpy(*d, v.data(), sizeof(int) * v.size(), cudaMemcpyHostToDevice));
   return PSP_OK;
 }
+static int upload_d(const std::vector<double> &v, double **d) {
+  size_t bytes = sizeof(double) * (v.size() ? v.size() : 1);
+  if (cudaMalloc((void **)d, bytes) != cudaSuccess) { cudaGetLastError(); set_error("out of device memory"); return PSP_ERR_NOMEM; }
+  if (!v.empty()) PSP_CUDA(cudaMemcpy(*d, v.data(), sizeof(double) * v.size(), cudaMemcpyHostToDevice));
+  return PSP_OK;
+}
 
-// level sets + level-sorted row lists (counting sort: rows ascending inside a level)
-static void sort_by_level(const std::vector<int> &level, int nlev, std::vector<int> &rows, std::vector<int> &lptr) {
+// level-sorted row lists (counting sort: rows ascending inside a level); returns the widest level
+static int sort_by_level(const std::vector<int> &level, int nlev, std::vector<int> &rows, std::vector<int> &lptr) {
   const int n = (int)level.size();
   lptr.assign((size_t)nlev + 1, 0);
   for (int i = 0; i < n; i++) lptr[level[i] + 1]++;
-  for (int l = 0; l < nlev; l++) lptr[l + 1] += lptr[l];
+  int maxw = 0;
+  for (int l = 0; l < nlev; l++) { if (lptr[l + 1] > maxw) maxw = lptr[l + 1]; lptr[l + 1] += lptr[l]; }
   std::vector<int> fill(lptr.begin(), lptr.end() - 1);
   rows.resize((size_t)n);
   for (int i = 0; i < n; i++) rows[fill[level[i]]++] = i;
+  return maxw;
+}
+
+// level-major copy of a CSR structure: position p holds row rows[p].  oloc[k] is the
+// position of column ocol[k] inside its level when that level is the one just before
+// the row's level (its x value is then still in shared memory), else -1.
+static void level_major(const std::vector<int> &rows, const std::vector<int> &lptr, const std::vector<int> &level,
+                        const std::vector<int> &ind, const std::vector<int> &col, const std::vector<double> &val,
+                        std::vector<int> &oind, std::vector<int> &ocol, std::vector<double> &oval,
+                        std::vector<int> &oloc) {
+  const size_t n = rows.size();
+  std::vector<int> pos(n);
+  for (size_t p = 0; p < n; p++) pos[rows[p]] = (int)p;
+  oind.assign(n + 1, 0);
+  ocol.resize(col.size());
+  oval.resize(val.size());
+  oloc.resize(col.size());
+  int q = 0;
+  for (size_t p = 0; p < n; p++) {
+    const int r = rows[p];
+    for (int k = ind[r]; k < ind[r + 1]; k++) {
+      const int c = col[k];
+      ocol[q] = c; oval[q] = val[k];
+      oloc[q] = (level[c] == level[r] - 1) ? pos[c] - lptr[level[c]] : -1;
+      q++;
+    }
+    oind[p + 1] = q;
+  }
 }
 
 int ssor_create(psp_mat *A, double omega, int steps, psp_prec **out) {
@@ -216,14 +511,6 @@ int ssor_create(psp_mat *A, double omega, int steps, psp_prec **out) {
   }
   if (n == 0) { nlf = 0; nlb = 0; }
   K->nlev_f = nlf; K->nlev_b = nlb;
-  std::vector<int> rows, lptr;
-  int st = PSP_OK;
-  sort_by_level(lf, nlf, rows, lptr);
-  if (st == PSP_OK) st = upload_i(rows, &K->d_rows_f);
-  if (st == PSP_OK) st = upload_i(lptr, &K->d_lptr_f);
-  sort_by_level(lb, nlb, rows, lptr);
-  if (st == PSP_OK) st = upload_i(rows, &K->d_rows_b);
-  if (st == PSP_OK) st = upload_i(lptr, &K->d_lptr_b);
   // transpose index of L, entries of each row by descending original row
   const size_t nnz = col.size();
   std::vector<int> tind((size_t)n + 1, 0), tcol(nnz), fill((size_t)(n > 0 ? n : 1));
@@ -233,13 +520,26 @@ int ssor_create(psp_mat *A, double omega, int steps, psp_prec **out) {
   for (int j = 0; j < n; j++) fill[j] = tind[j];
   for (int i = n - 1; i >= 0; i--)
     for (int k = ind[i]; k < ind[i + 1]; k++) { int j = col[k]; tcol[fill[j]] = i; tval[fill[j]] = val[k]; fill[j]++; }
-  if (st == PSP_OK) st = upload_i(tind, &K->d_tind);
-  if (st == PSP_OK) st = upload_i(tcol, &K->d_tcol);
-  if (st == PSP_OK) {
-    size_t bytes = sizeof(double) * (nnz ? nnz : 1);
-    if (cudaMalloc((void **)&K->d_tval, bytes) != cudaSuccess) { cudaGetLastError(); st = PSP_ERR_NOMEM; }
-    else if (nnz && cudaMemcpy(K->d_tval, tval.data(), sizeof(double) * nnz, cudaMemcpyHostToDevice) != cudaSuccess) st = PSP_ERR_CUDA;
-  }
+
+  std::vector<int> rows, lptr, oind, ocol, oloc;
+  std::vector<double> oval;
+  int st = PSP_OK;
+  K->maxw_f = sort_by_level(lf, nlf, rows, lptr);
+  level_major(rows, lptr, lf, ind, col, val, oind, ocol, oval, oloc);
+  if (st == PSP_OK) st = upload_i(oloc, &K->d_floc);
+  if (st == PSP_OK) st = upload_i(rows, &K->d_rows_f);
+  if (st == PSP_OK) st = upload_i(lptr, &K->d_lptr_f);
+  if (st == PSP_OK) st = upload_i(oind, &K->d_find);
+  if (st == PSP_OK) st = upload_i(ocol, &K->d_fcol);
+  if (st == PSP_OK) st = upload_d(oval, &K->d_fval);
+  K->maxw_b = sort_by_level(lb, nlb, rows, lptr);
+  level_major(rows, lptr, lb, tind, tcol, tval, oind, ocol, oval, oloc);
+  if (st == PSP_OK) st = upload_i(oloc, &K->d_bloc);
+  if (st == PSP_OK) st = upload_i(rows, &K->d_rows_b);
+  if (st == PSP_OK) st = upload_i(lptr, &K->d_lptr_b);
+  if (st == PSP_OK) st = upload_i(oind, &K->d_bind);
+  if (st == PSP_OK) st = upload_i(ocol, &K->d_bcol);
+  if (st == PSP_OK) st = upload_d(oval, &K->d_bval);
   if (st == PSP_OK && cudaMalloc((void **)&K->d_t1, sizeof(double) * (size_t)(n > 0 ? n : 1)) != cudaSuccess) {
     cudaGetLastError(); st = PSP_ERR_NOMEM;
   }
@@ -293,7 +593,8 @@ extern "C" void psp_prec_destroy(psp_prec *K) {
   if (!K) return;
   cudaFree(K->d_dinv); cudaFree(K->d_t1); cudaFree(K->d_t2);
   cudaFree(K->d_rows_f); cudaFree(K->d_lptr_f); cudaFree(K->d_rows_b); cudaFree(K->d_lptr_b);
-  cudaFree(K->d_tind); cudaFree(K->d_tcol); cudaFree(K->d_tval);
+  cudaFree(K->d_find); cudaFree(K->d_fcol); cudaFree(K->d_fval);
+  cudaFree(K->d_bind); cudaFree(K->d_bcol); cudaFree(K->d_bval); cudaFree(K->d_floc); cudaFree(K->d_bloc);
   cudaFree(K->d_x); cudaFree(K->d_y); cudaFree(K->d_bar);
   delete K;
 }

@@ -239,6 +239,8 @@ extern "C" int psp_set_option(const char *name, long long value) {
   else if (!strcmp(name, "use_graph")) c.use_graph = value;
   else if (!strcmp(name, "l2_stream")) c.l2_stream = value;
   else if (!strcmp(name, "pcg_persist")) c.pcg_persist = value;
+  else if (!strcmp(name, "ssor_engine")) c.ssor_engine = value;
+  else if (!strcmp(name, "ssor_cluster")) c.ssor_cluster = (value >= 1 && value <= 16) ? value : 8;
   else { set_error("unknown option '%s'", name); return PSP_ERR_ARG; }
   return PSP_OK;
 }
