@@ -110,6 +110,7 @@ struct Ring {
   // can be done long before the vector to multiply is ready).  All threads call it.
   __device__ __forceinline__ void prefetch(const MatView &A) {
     if (threadIdx.x == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // see pass(): in-place products
 #pragma unroll
       for (int s = 0; s < STAGES; s++) {
         const int b = blockIdx.x + s * gridDim.x;
@@ -150,6 +151,7 @@ struct Ring {
       const int2 d0 = __ldg(A.blk + b), d1 = __ldg(A.blk + b + 1);
       const int r0 = d0.x, r1 = d1.x, k0 = d0.y, k1 = d1.y;
       const int nrows = r1 - r0, cnt = k1 - k0;
+      bool wrote_stage = false;                     // stage buffer was written through the generic proxy
       if (cnt <= kBlkNnz) {
         const unsigned char *st = smem + (size_t)stage * kStageBytes;
         const double *sval = reinterpret_cast<const double *>(st);
@@ -175,7 +177,12 @@ struct Ring {
             rowop(r0 + tid, sum);
           }
         } else {
-          // long rows: one warp per row
+          // longer rows: a group of 8 / 16 / 32 lanes per row, chosen from the block's mean
+          // row length so that a CTA keeps 32 / 16 / 8 rows (and their x gathers) in flight
+          // longer rows: one warp per row.  (Measured alternatives on the 2^22-row power-law
+          // matrix, 1118 us: 8-lane groups per row 1331 us; entry-parallel products in place +
+          // segmented sums 1208 us -- the kernel is bound by the 32-byte L2 sectors fetched
+          // per 8-byte random x gather, not by how the rows are mapped to lanes.)
           const int w = tid >> 5, l = tid & 31;
           for (int rr = w; rr < nrows; rr += kThreads / 32) {
             const int s = sind[roff + rr] - base, e = sind[roff + rr + 1] - base;
@@ -196,6 +203,9 @@ struct Ring {
       __syncthreads();                              // everyone is done with this stage's buffers
       if (tid == 0) {
         const int nb2 = b + STAGES * gridDim.x;
+        // our in-place writes (generic proxy) must be ordered before the TMA (async proxy)
+        // overwrites the same buffer
+        if (wrote_stage) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         if (nb2 < A.nb) issue(A, nb2, stage);
       }
     }

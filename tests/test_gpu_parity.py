@@ -184,7 +184,7 @@ def test_device_resident_solve_and_launch_counter(native):
     native.launch_count(reset=True)
     r1 = native.solve("pcg", S, db, dx, 1e-10, 1000, K, dev=True)
     native.set_option("pcg_persist", -1)
-    assert native.launch_count() == 2 and r1[:2] == r[:2] and abs(r1[2] - r[2]) <= 1e-12
+    assert native.launch_count() == 1 and r1[:2] == r[:2] and abs(r1[2] - r[2]) <= 1e-12
     x = dx.download()
     y = np.zeros(n); S.matvec(x, y)
     assert np.linalg.norm(1.0 - y) / np.sqrt(n) <= 1e-9
