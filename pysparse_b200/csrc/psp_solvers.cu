@@ -204,7 +204,7 @@ struct FPcgResid {          // r = b - r (r holds A x); sums r.r and r.(K^-1 r);
 };
 struct FPcgP {              // p = z + beta p   (first iteration: p = z), pcg.c:105-115
   static constexpr int NS = 0; static constexpr bool HASMAX = false, TICKET = false;
-  const double *z, *dinv; double *p; double beta; int first;
+  const double *__restrict__ z, *__restrict__ dinv; double *__restrict__ p; double beta; int first;
   __device__ void prepare(const State *S) { beta = S->v[V_BETA]; first = (S->it == 1); }
   __device__ void elem(long i, double *, double &) {
     double zi = dinv ? z[i] * dinv[i] : z[i];
@@ -213,7 +213,8 @@ struct FPcgP {              // p = z + beta p   (first iteration: p = z), pcg.c:
 };
 struct FPcgUpdate {         // stagnation scan, x += alpha p, r -= alpha q, |r|^2 (and r.K^-1 r)
   static constexpr int NS = 2; static constexpr bool HASMAX = true, TICKET = false;
-  const double *p, *q, *dinv; double *x, *r; double alpha; int scan;
+  const double *__restrict__ p, *__restrict__ q, *__restrict__ dinv; double *__restrict__ x, *__restrict__ r;
+  double alpha; int scan;
   __device__ void prepare(const State *S) { alpha = S->v[V_ALPHA]; scan = (S->stag == 0); }
   __device__ void elem(long i, double *acc, double &mx) {
     double xi = x[i], pi = p[i];
