@@ -215,6 +215,12 @@ int psp_dist_info(int *rank, int *world, size_t *slot_elems, int *nslots);
 /* This rank's slab: ind[nl+1], col_global[nnz], val[nnz] */
 int psp_dist_csr_create(const int *rowptr, int nnz, const int *ind, const int *col_global,
                         const double *val, psp_dmat **out);
+/* Optional send map (push model of the single-launch PCG kernel): entry s says that
+ * local row rows[s] must be stored at element dst_off[s] of the multiplied vector in
+ * rank dst_rank[s]'s heap (dst_off = that rank's local row count + its halo position).
+ * Without it the halo is pulled by the consumer. */
+int psp_dist_set_sendmap(psp_dmat *a, int nsend, const int *rows, const int *dst_rank,
+                         const int *dst_off);
 void psp_dist_mat_destroy(psp_dmat *a);
 int psp_dist_mat_info(const psp_dmat *a, int *nl, int *nhalo, unsigned *neighbour_mask);
 

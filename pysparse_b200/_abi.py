@@ -31,6 +31,7 @@ SYMBOLS = [
     "psp_event_record", "psp_event_elapsed_ms", "psp_spmv_timing",
     "psp_dist_plan", "psp_dist_init", "psp_dist_connect", "psp_dist_shutdown", "psp_dist_info",
     "psp_dist_csr_create", "psp_dist_mat_destroy", "psp_dist_mat_info", "psp_dist_solve_dev",
+    "psp_dist_set_sendmap",
 ]
 
 SOLVERS = {"pcg": 0, "minres": 1, "qmrs": 2, "bicgstab": 3, "cgs": 4, "gmres": 5}

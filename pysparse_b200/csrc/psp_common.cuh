@@ -60,7 +60,8 @@ struct DistMail {                       // one all-reduce contribution
 
 struct DistCtl {                        // lives in each rank's IPC-shared control block
   unsigned long long pub;               // number of vector publications completed by this rank
-  unsigned long long pad[15];
+  unsigned long long pad[7];
+  unsigned long long arrived[kMaxRanks];  // push model: arrived[w] = halo pushes rank w has completed into THIS rank
   DistMail mail[kMailRing][kMaxRanks];  // mail[seq % ring][source rank]
 };
 
@@ -71,6 +72,7 @@ struct DistDev {                        // device-resident descriptor (private t
   unsigned long long red_seq;           // reductions performed so far (identical on all ranks)
   unsigned long long pubs_done;         // publications performed by this rank
   unsigned long long pulls_done;        // halo pulls performed by this rank
+  unsigned push_ticket;                 // CTAs of the persistent kernel that finished their halo pushes
 };
 
 struct State {
@@ -115,6 +117,8 @@ struct Ctx {
   long long pcg_persist = -1; // single-launch PCG: 1 always, 0 never, -1 automatic
   long long ssor_engine = 0;  // SSOR sweeps: 0 automatic, 1 grid-wide barrier, 2 cluster barrier
   long long ssor_cluster = 8; // CTAs in the sweep cluster (8 portable, 16 non-portable)
+  long long dist_push = 1;    // sharded single-launch PCG: push the halo to the neighbours (needs the send map)
+  long long dist_debug = 0;   // timing diagnostics only (results invalid): 1 skip halo pull, 2 also skip the cross-GPU all-reduce
   long long poll_chunk = 0;   // 0: automatic
   long long use_graph = 1;
   // sampled SpMV timing (bench.py roofline): event pairs around every Nth launch

@@ -177,7 +177,7 @@ extern "C" int psp_dist_info(int *rank, int *world, size_t *slot_elems, int *nsl
 
 // ------------------------------------------------------------------ distributed matrix
 namespace psp {
-int csr_create(int, int, long long, const int *, const int *, const double *, psp_mat **, bool);
+int csr_create(int, int, long long, const int *, const int *, const double *, psp_mat **, bool, int);
 }
 
 extern "C" int psp_dist_csr_create(const int *rowptr, int nnz, const int *ind, const int *col_global,
@@ -197,7 +197,7 @@ extern "C" int psp_dist_csr_create(const int *rowptr, int nnz, const int *ind, c
   }
   DistMat *dm = new DistMat();
   dm->nl = nl; dm->nhalo = nhalo; dm->nglobal = rowptr[d.world];
-  int st = csr_create(nl, nl + nhalo, nnz, ind, col_local.data(), val, &dm->local, false);
+  int st = csr_create(nl, nl + nhalo, nnz, ind, col_local.data(), val, &dm->local, false, nl);
   if (st != PSP_OK) { delete dm; return st; }
   dm->nbmask = 0;
   for (int h = 0; h < nhalo; h++) dm->nbmask |= 1u << owner[h];
@@ -216,11 +216,53 @@ extern "C" int psp_dist_csr_create(const int *rowptr, int nnz, const int *ind, c
   return PSP_OK;
 }
 
+// Send map for the push model: entry s says "local row rows[s] is halo column number
+// off[s] - nl(dst) of rank dst_rank[s]", i.e. it has to be stored at element off[s] of the
+// multiplied vector in that rank's heap.  Built by the launcher from the all-gathered
+// halo lists (pysparse_b200/dist.py); integer work, verified against psp_dist_plan.
+extern "C" int psp_dist_set_sendmap(psp_dmat *m, int nsend, const int *rows, const int *dst_rank,
+                                    const int *dst_off) {
+  DistMat *dm = (DistMat *)m;
+  DistHost &d = g_dist;
+  if (!dm || nsend < 0 || (nsend > 0 && (!rows || !dst_rank || !dst_off))) {
+    set_error("psp_dist_set_sendmap: bad arguments");
+    return PSP_ERR_ARG;
+  }
+  unsigned mask = 0;
+  for (int s = 0; s < nsend; s++) {
+    if (rows[s] < 0 || rows[s] >= dm->nl || dst_rank[s] < 0 || dst_rank[s] >= d.world || dst_rank[s] == d.rank ||
+        dst_off[s] < 0 || (size_t)dst_off[s] >= d.slot_elems) {
+      set_error("psp_dist_set_sendmap: entry %d out of range", s);
+      return PSP_ERR_ARG;
+    }
+    mask |= 1u << dst_rank[s];
+  }
+  cudaFree(dm->d_send_row); cudaFree(dm->d_send_rank); cudaFree(dm->d_send_off);
+  dm->d_send_row = dm->d_send_rank = dm->d_send_off = nullptr;
+  const size_t bytes = sizeof(int) * (size_t)(nsend > 0 ? nsend : 1);
+  if (cudaMalloc((void **)&dm->d_send_row, bytes) != cudaSuccess || cudaMalloc((void **)&dm->d_send_rank, bytes) != cudaSuccess ||
+      cudaMalloc((void **)&dm->d_send_off, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    set_error("psp_dist_set_sendmap: out of device memory");
+    return PSP_ERR_NOMEM;
+  }
+  if (nsend) {
+    PSP_CUDA(cudaMemcpy(dm->d_send_row, rows, sizeof(int) * (size_t)nsend, cudaMemcpyHostToDevice));
+    PSP_CUDA(cudaMemcpy(dm->d_send_rank, dst_rank, sizeof(int) * (size_t)nsend, cudaMemcpyHostToDevice));
+    PSP_CUDA(cudaMemcpy(dm->d_send_off, dst_off, sizeof(int) * (size_t)nsend, cudaMemcpyHostToDevice));
+  }
+  dm->nsend = nsend;
+  dm->sendmask = mask;
+  dm->has_sendmap = true;
+  return PSP_OK;
+}
+
 extern "C" void psp_dist_mat_destroy(psp_dmat *m) {
   DistMat *dm = (DistMat *)m;
   if (!dm) return;
   if (dm->local) psp_mat_destroy(dm->local);
   cudaFree(dm->d_owner); cudaFree(dm->d_ridx);
+  cudaFree(dm->d_send_row); cudaFree(dm->d_send_rank); cudaFree(dm->d_send_off);
   delete dm;
 }
 

@@ -21,6 +21,11 @@ struct DistMat {
   int nl = 0, nhalo = 0, nglobal = 0;
   int *d_owner = nullptr, *d_ridx = nullptr;
   unsigned nbmask = 0;                    // ranks this rank pulls halo values from
+  // push model (persistent kernels): local rows other ranks need, and where they go
+  int nsend = 0;
+  int *d_send_row = nullptr, *d_send_rank = nullptr, *d_send_off = nullptr;
+  unsigned sendmask = 0;                  // ranks this rank pushes halo values to
+  bool has_sendmap = false;
 };
 
 DistHost &dist();

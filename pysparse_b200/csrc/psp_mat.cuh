@@ -15,6 +15,7 @@ struct psp_mat {
   double *d_val = nullptr;
   // row-block schedule of the streaming SpMV kernel
   int nb = 0;
+  int nint = 0;             // leading blocks that read no halo column (== nb unless sharded)
   int *d_blk = nullptr;
   // SSS originals (strict lower CSR + diagonal), kept for the SSOR sweeps
   int *d_lind = nullptr, *d_lcol = nullptr;

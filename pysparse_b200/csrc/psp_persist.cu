@@ -40,10 +40,15 @@ struct PcgArgs {
   State *S;
   double *partials;             // 2 x (kRedSlots + 1) x kMaxGrid, double-buffered
   int l2_stream;
+  int dist_debug;               // timing diagnostics (see Ctx::dist_debug)
   // multi-GPU
   const int *halo_owner, *halo_ridx;
   int nhalo;
   unsigned nbmask;
+  // push model (send map present)
+  int push, nsend;
+  const int *send_row, *send_rank, *send_off;
+  unsigned sendmask;
 };
 
 struct PersistCtx {
@@ -54,6 +59,7 @@ struct PersistCtx {
   DistDev *dd;
   unsigned long long seq, pubs, pulls;
   int parity;
+  int debug;
 };
 
 // Grid-wide deterministic reduction; on return tot[0..NS) (and tot[kRedSlots] for the
@@ -87,7 +93,7 @@ __device__ __forceinline__ void grid_allreduce(cg::grid_group &grid, PersistCtx 
     if (threadIdx.x == 0) c.tot[kRedSlots] = a;
   }
   __syncthreads();
-  if (c.dd) {
+  if (c.dd && c.debug < 2) {
     // cross-GPU: CTA 0 pushes this rank's totals to every peer's mailbox; every CTA
     // reads the W contributions from the LOCAL mailbox and adds them in rank order
     __shared__ double box[kMaxRanks][kRedSlots + 1];
@@ -144,6 +150,7 @@ __device__ __forceinline__ void epilogue(PersistCtx &c, int id) {
 __device__ __forceinline__ void publish_and_pull(cg::grid_group &grid, PersistCtx &c, const PcgArgs &a, double *vec,
                                                  size_t slot_off) {
   DistDev *dd = c.dd;
+  if (c.debug >= 1) { grid.sync(); return; }
   c.pubs += 1;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     __threadfence_system();
@@ -163,6 +170,46 @@ __device__ __forceinline__ void publish_and_pull(cg::grid_group &grid, PersistCt
   grid.sync();
 }
 
+// Push model (needs the send map, psp_dist_set_sendmap): called after the grid barrier
+// that completes `vec`.  Every thread stores its share of the boundary entries straight
+// into the neighbours' heaps (posted NVLink stores, nobody waits for them); the CTA that
+// finishes last raises the "arrived" counters in the neighbours' control blocks; then the
+// CTA waits -- on LOCAL memory -- until its own neighbours' entries have arrived.  No
+// remote loads, no second grid barrier.  The wait (halo_wait) is deferred to the first
+// row block that reads a halo column, so the transfer overlaps the interior blocks.
+__device__ __forceinline__ void halo_push(PersistCtx &c, const PcgArgs &a, const double *vec, size_t slot_off) {
+  DistDev *dd = c.dd;
+  const int me = dd->rank;
+  c.pubs += 1;
+  c.pulls += 1;
+  if (c.debug >= 1) return;
+  const int stride = gridDim.x * blockDim.x;
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < a.nsend; s += stride)
+    st_relaxed_sys_f64(dd->heap[a.send_rank[s]] + slot_off + a.send_off[s], vec[a.send_row[s]]);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    const unsigned t = atomicAdd(&dd->push_ticket, 1u);
+    if (t == gridDim.x - 1) {
+      dd->push_ticket = 0u;
+      __threadfence_system();
+      for (int w = 0; w < dd->world; w++)
+        if ((a.sendmask >> w) & 1u) st_release_sys(&dd->ctl[w]->arrived[me], c.pubs);
+    }
+  }
+}
+
+__device__ __forceinline__ void halo_wait(PersistCtx &c, const PcgArgs &a) {
+  DistDev *dd = c.dd;
+  if (c.debug >= 1) return;
+  if (threadIdx.x == 0) {
+    for (int w = 0; w < dd->world; w++)
+      if ((a.nbmask >> w) & 1u)
+        while (ld_acquire_sys(&dd->ctl[dd->rank]->arrived[w]) < c.pulls) { }
+  }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(kThreads, 4) k_pcg_persist(PcgArgs a, size_t p_slot_off) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t full[kPersistStages];
@@ -180,6 +227,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_pcg_persist(PcgArgs a, size_t p
   PersistCtx c;
   c.sS = &sS; c.tot = tot; c.red_sh = red_sh; c.partials = a.partials; c.parity = 0;
   c.dd = sS.dist;
+  c.debug = a.dist_debug;
   c.seq = c.pubs = c.pulls = 0;
   if (c.dd) { c.seq = c.dd->red_seq; c.pubs = c.dd->pubs_done; c.pulls = c.dd->pulls_done; }
 
@@ -199,10 +247,12 @@ __global__ void __launch_bounds__(kThreads, 4) k_pcg_persist(PcgArgs a, size_t p
   if (c.dd) {
     for (long i = g0; i < n; i += gstride) a.p[i] = a.x[i];
     grid.sync();
-    publish_and_pull(grid, c, a, a.p, p_slot_off);
+    if (a.push) halo_push(c, a, a.p, p_slot_off);
+    else publish_and_pull(grid, c, a, a.p, p_slot_off);
     xin = a.p;
   }
-  ring.template pass<false>(a.A, xin, red_sh, [&](int r, double sum) { a.r[r] = sum; });
+  ring.template pass<false>(a.A, xin, red_sh, [&](int r, double sum) { a.r[r] = sum; },
+                            [&] { if (a.push) halo_wait(c, a); });
   ring.prefetch(a.A);
   grid.sync();
   {
@@ -232,10 +282,14 @@ __global__ void __launch_bounds__(kThreads, 4) k_pcg_persist(PcgArgs a, size_t p
       }
     }
     grid.sync();
-    if (c.dd) publish_and_pull(grid, c, a, a.p, p_slot_off);
+    if (c.dd) {
+      if (a.push) halo_push(c, a, a.p, p_slot_off);
+      else publish_and_pull(grid, c, a, a.p, p_slot_off);
+    }
     {                                   // q = A p ; pq = p.q
       double acc[1] = {0.0};
-      ring.template pass<false>(a.A, a.p, red_sh, [&](int r, double sum) { a.q[r] = sum; acc[0] += a.p[r] * sum; });
+      ring.template pass<false>(a.A, a.p, red_sh, [&](int r, double sum) { a.q[r] = sum; acc[0] += a.p[r] * sum; },
+                                [&] { if (a.push) halo_wait(c, a); });
       ring.prefetch(a.A);
       grid_allreduce<1, false>(grid, c, acc, 0.0);
       epilogue<1, false>(c, EPI_PCG_PQ);
@@ -289,11 +343,16 @@ int pcg_persist_launch(const psp_mat *M, int n, const double *b, double *x, doub
   if (!g_partials2) PSP_CUDA(cudaMalloc((void **)&g_partials2, sizeof(double) * 2 * (kRedSlots + 1) * kMaxGrid));
   PcgArgs a;
   a.A.ind = M->d_ind; a.A.col = M->d_col; a.A.val = M->d_val; a.A.nb = M->nb;
-  a.A.blk = reinterpret_cast<const int2 *>(M->d_blk);
+  a.A.blk = reinterpret_cast<const int4 *>(M->d_blk);
+  a.A.nint = M->nint;
   a.n = n; a.b = b; a.x = x; a.r = r; a.p = p; a.q = q; a.dinv = dinv;
-  a.S = c.state; a.partials = g_partials2; a.l2_stream = l2_stream_for(n);
+  a.S = c.state; a.partials = g_partials2; a.l2_stream = l2_stream_for(n); a.dist_debug = (int)c.dist_debug;
   a.halo_owner = dm ? dm->d_owner : nullptr; a.halo_ridx = dm ? dm->d_ridx : nullptr;
   a.nhalo = dm ? dm->nhalo : 0; a.nbmask = dm ? dm->nbmask : 0u;
+  a.push = (dm && dm->has_sendmap && c.dist_push) ? 1 : 0;
+  a.nsend = dm ? dm->nsend : 0; a.sendmask = dm ? dm->sendmask : 0u;
+  a.send_row = dm ? dm->d_send_row : nullptr; a.send_rank = dm ? dm->d_send_rank : nullptr;
+  a.send_off = dm ? dm->d_send_off : nullptr;
   size_t p_slot_off = dm ? (size_t)(p - dist().heap) : 0;
   // enough CTAs for the vector phases and the row blocks, never more than are co-resident
   long long want = (n + kThreads - 1) / kThreads;

@@ -240,6 +240,8 @@ extern "C" int psp_set_option(const char *name, long long value) {
   else if (!strcmp(name, "l2_stream")) c.l2_stream = value;
   else if (!strcmp(name, "pcg_persist")) c.pcg_persist = value;
   else if (!strcmp(name, "ssor_engine")) c.ssor_engine = value;
+  else if (!strcmp(name, "dist_debug")) c.dist_debug = value;
+  else if (!strcmp(name, "dist_push")) c.dist_push = value;
   else if (!strcmp(name, "ssor_cluster")) c.ssor_cluster = (value >= 1 && value <= 16) ? value : 8;
   else { set_error("unknown option '%s'", name); return PSP_ERR_ARG; }
   return PSP_OK;
@@ -253,5 +255,11 @@ extern "C" long long psp_get_option(const char *name) {
   if (!strcmp(name, "poll_chunk")) return c.poll_chunk;
   if (!strcmp(name, "use_graph")) return c.use_graph;
   if (!strcmp(name, "sms")) return c.sms;
+  if (!strcmp(name, "l2_stream")) return c.l2_stream;
+  if (!strcmp(name, "pcg_persist")) return c.pcg_persist;
+  if (!strcmp(name, "ssor_engine")) return c.ssor_engine;
+  if (!strcmp(name, "ssor_cluster")) return c.ssor_cluster;
+  if (!strcmp(name, "dist_debug")) return c.dist_debug;
+  if (!strcmp(name, "dist_push")) return c.dist_push;
   return -1;
 }

@@ -68,9 +68,8 @@ __global__ void __launch_bounds__(kThreads, 4) k_spmv_stream(SpmvArgs a) {
   double acc0 = 0.0, acc1 = 0.0;
 
   for (int b = blockIdx.x; b < a.nb; b += gridDim.x) {
-    const int2 d0 = __ldg(reinterpret_cast<const int2 *>(a.blk) + b);
-    const int2 d1 = __ldg(reinterpret_cast<const int2 *>(a.blk) + b + 1);
-    const int r0 = d0.x, r1 = d1.x, k0 = d0.y, k1 = d1.y;
+    const int4 d = __ldg(reinterpret_cast<const int4 *>(a.blk) + b);
+    const int r0 = d.x, r1 = d.z, k0 = d.y, k1 = d.w;
     const int nrows = r1 - r0, cnt = k1 - k0;
 
     if (cnt <= kBlkNnz) {
@@ -187,8 +186,8 @@ __global__ void __launch_bounds__(kThreads) k_spmv_tma(SpmvArgs a) {
     if (V->done || (a.gate == 1 && V->cyc_done)) return;
   }
   MatView A;
-  A.ind = a.ind; A.col = a.col; A.val = a.val; A.nb = a.nb;
-  A.blk = reinterpret_cast<const int2 *>(a.blk);
+  A.ind = a.ind; A.col = a.col; A.val = a.val; A.nb = a.nb; A.nint = a.nb;
+  A.blk = reinterpret_cast<const int4 *>(a.blk);
   Ring<STAGES> ring;
   ring.init(smem, full, a.l2_stream != 0);
   double acc0 = 0.0, acc1 = 0.0;
@@ -284,12 +283,33 @@ static int check_csr(int m, int n, long long nnz, const int *ind, const int *col
   return PSP_OK;
 }
 
-static int finish_csr_upload(psp_mat *A, const std::vector<int> &ind, const int *col, const double *val) {
-  std::vector<int> rows, blk;
+// own_cols >= 0 (row slab of a sharded matrix, halo columns numbered from own_cols on):
+// the blocks that touch no halo column are scheduled first, A->nint of them.
+static int finish_csr_upload(psp_mat *A, const std::vector<int> &ind, const int *col, const double *val,
+                             int own_cols = -1) {
+  std::vector<int> rows, blk, order;
   build_row_blocks(A->m, ind.data(), rows);
   A->nb = (int)rows.size() - 1;
-  blk.resize(2 * rows.size());          // (first row, first entry) per block + sentinel
-  for (size_t i = 0; i < rows.size(); i++) { blk[2 * i] = rows[i]; blk[2 * i + 1] = ind[rows[i]]; }
+  A->nint = A->nb;
+  order.reserve((size_t)A->nb);
+  if (own_cols >= 0) {
+    std::vector<int> boundary;
+    for (int b = 0; b < A->nb; b++) {
+      bool halo = false;
+      for (int k = ind[rows[b]]; k < ind[rows[b + 1]] && !halo; k++) halo = col[k] >= own_cols;
+      (halo ? boundary : order).push_back(b);
+    }
+    A->nint = (int)order.size();
+    order.insert(order.end(), boundary.begin(), boundary.end());
+  } else {
+    for (int b = 0; b < A->nb; b++) order.push_back(b);
+  }
+  blk.resize(4 * (size_t)A->nb);        // (first row, first entry, end row, end entry) per block
+  for (int i = 0; i < A->nb; i++) {
+    const int b = order[i];
+    blk[4 * i] = rows[b]; blk[4 * i + 1] = ind[rows[b]];
+    blk[4 * i + 2] = rows[b + 1]; blk[4 * i + 3] = ind[rows[b + 1]];
+  }
   PSP_TRY(upload(ind.data(), sizeof(int) * (size_t)(A->m + 1), (void **)&A->d_ind));
   PSP_TRY(upload(col, sizeof(int) * (size_t)A->fnnz, (void **)&A->d_col));
   PSP_TRY(upload(val, sizeof(double) * (size_t)A->fnnz, (void **)&A->d_val));
@@ -299,12 +319,12 @@ static int finish_csr_upload(psp_mat *A, const std::vector<int> &ind, const int 
 }
 
 int csr_create(int m, int n, long long nnz, const int *ind, const int *col, const double *val,
-               psp_mat **out, bool keep_host) {
+               psp_mat **out, bool keep_host, int own_cols) {
   PSP_TRY(check_csr(m, n, nnz, ind, col, false));
   psp_mat *A = new psp_mat();
   A->kind = 1; A->m = m; A->n = n; A->nnz = nnz; A->fnnz = nnz;
   std::vector<int> hind(ind, ind + m + 1);
-  int st = finish_csr_upload(A, hind, col, val);
+  int st = finish_csr_upload(A, hind, col, val, own_cols);
   if (st != PSP_OK) { psp_mat_destroy(A); return st; }
   if (keep_host) {
     A->h_ind.swap(hind);
@@ -383,7 +403,7 @@ int mat_transpose(psp_mat *A) {
       tcol[fill[j]] = i; tval[fill[j]] = val[k]; fill[j]++;
     }
   psp_mat *T = nullptr;
-  PSP_TRY(csr_create(n, m, nnz, tind.data(), tcol.data(), tval.data(), &T, false));
+  PSP_TRY(csr_create(n, m, nnz, tind.data(), tcol.data(), tval.data(), &T, false, -1));
   A->transp = T;
   return PSP_OK;
 }
@@ -459,7 +479,7 @@ static int spmv_dispatch(const psp_mat *A, const double *dx, double *dy, const S
 using namespace psp;
 
 namespace psp {
-int csr_create(int, int, long long, const int *, const int *, const double *, psp_mat **, bool);
+int csr_create(int, int, long long, const int *, const int *, const double *, psp_mat **, bool, int);
 int sss_create(int, long long, const int *, const int *, const double *, const double *, psp_mat **);
 }
 
@@ -467,7 +487,7 @@ extern "C" int psp_csr_create(int m, int n, int nnz, const int *ind, const int *
                               const double *val, psp_mat **out) {
   if (!out || !ind || (nnz > 0 && (!col || !val))) { set_error("psp_csr_create: NULL argument"); return PSP_ERR_ARG; }
   PSP_TRY(ensure_init());
-  return csr_create(m, n, nnz, ind, col, val, out, false);
+  return csr_create(m, n, nnz, ind, col, val, out, false, -1);
 }
 
 extern "C" int psp_sss_create(int n, int nnz, const int *ind, const int *col, const double *val,

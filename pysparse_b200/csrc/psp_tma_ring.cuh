@@ -60,9 +60,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 
 struct MatView {                          // device view of a CSR matrix + its row-block schedule
   const int *ind, *col;
-  const int2 *blk;                        // (first row, first entry) per block, nb + 1 entries
+  const int4 *blk;                        // (first row, first entry, end row, end entry) per block
   const double *val;
   int nb;
+  int nint;                               // blocks [nint, nb) read halo columns (sharded matrices; else nb)
 };
 
 template <int STAGES>
@@ -87,11 +88,11 @@ struct Ring {
 
   // thread 0 only: start the bulk copies of row block b into `stage`
   __device__ __forceinline__ void issue(const MatView &A, int b, int stage) {
-    const int2 d0 = __ldg(A.blk + b), d1 = __ldg(A.blk + b + 1);
-    if (d1.y - d0.y > kBlkNnz) return;              // over-long row: read straight from global
-    const int base = d0.y & ~3, rbase = d0.x & ~3;
-    const uint32_t ne = (uint32_t)((d1.y - base + 3) & ~3);
-    const uint32_t nr = (uint32_t)((d1.x + 1 - rbase + 3) & ~3);
+    const int4 d = __ldg(A.blk + b);
+    if (d.w - d.y > kBlkNnz) return;                // over-long row: read straight from global
+    const int base = d.y & ~3, rbase = d.x & ~3;
+    const uint32_t ne = (uint32_t)((d.w - base + 3) & ~3);
+    const uint32_t nr = (uint32_t)((d.z + 1 - rbase + 3) & ~3);
     unsigned char *st = smem + (size_t)stage * kStageBytes;
     mbar_expect_tx(&full[stage], ne * 12u + nr * 4u);
     if (policy) {
@@ -126,8 +127,8 @@ struct Ring {
     for (int s = 0; s < STAGES; s++) {
       const int b = blockIdx.x + s * gridDim.x;
       if (b >= A.nb) break;
-      const int2 d0 = __ldg(A.blk + b), d1 = __ldg(A.blk + b + 1);
-      if (d1.y - d0.y > kBlkNnz) continue;
+      const int4 d = __ldg(A.blk + b);
+      if (d.w - d.y > kBlkNnz) continue;
       const int stage = (cursor + s) % STAGES;
       mbar_wait(&full[stage], (phases >> stage) & 1u);
       phases ^= (1u << stage);
@@ -140,16 +141,27 @@ struct Ring {
   // NC: gather x through the non-coherent read-only path (ld.global.nc) -- only legal
   // when x is not written during the kernel; the persistent kernels, which rewrite x
   // between grid barriers, use ordinary loads.
+  //
+  // The schedule lists the blocks that touch no halo column first (MatView::nint of
+  // them); haloop() is called once, by all threads, before this CTA's first block that
+  // does -- the sharded persistent kernels wait there for the neighbours' boundary
+  // values, which have been travelling while the interior blocks were multiplied.
   template <bool NC, class RowOp>
   __device__ __forceinline__ void pass(const MatView &A, const double *x, double *red_sh, RowOp rowop) {
+    pass<NC>(A, x, red_sh, rowop, [] {});
+  }
+  template <bool NC, class RowOp, class HaloOp>
+  __device__ __forceinline__ void pass(const MatView &A, const double *x, double *red_sh, RowOp rowop, HaloOp haloop) {
     const int tid = threadIdx.x;
     if (!prefetched) prefetch(A);
     prefetched = 0;
+    bool halo_ready = false;
     for (int b = blockIdx.x; b < A.nb; b += gridDim.x) {
+      if (!halo_ready && b >= A.nint) { haloop(); halo_ready = true; }
       const int stage = cursor;
       cursor = (cursor + 1) % STAGES;
-      const int2 d0 = __ldg(A.blk + b), d1 = __ldg(A.blk + b + 1);
-      const int r0 = d0.x, r1 = d1.x, k0 = d0.y, k1 = d1.y;
+      const int4 d = __ldg(A.blk + b);
+      const int r0 = d.x, r1 = d.z, k0 = d.y, k1 = d.w;
       const int nrows = r1 - r0, cnt = k1 - k0;
       bool wrote_stage = false;                     // stage buffer was written through the generic proxy
       if (cnt <= kBlkNnz) {

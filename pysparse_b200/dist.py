@@ -22,6 +22,7 @@ P.lib.psp_dist_init.argtypes = [C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_void_
 P.lib.psp_dist_connect.argtypes = [C.c_void_p]
 P.lib.psp_dist_info.argtypes = [_ip, _ip, C.POINTER(C.c_size_t), _ip]
 P.lib.psp_dist_csr_create.argtypes = [_ip, C.c_int, _ip, _ip, _dp, C.POINTER(C.c_void_p)]
+P.lib.psp_dist_set_sendmap.argtypes = [C.c_void_p, C.c_int, _ip, _ip, _ip]
 P.lib.psp_dist_mat_destroy.argtypes = [C.c_void_p]
 P.lib.psp_dist_mat_destroy.restype = None
 P.lib.psp_dist_mat_info.argtypes = [C.c_void_p, _ip, _ip, C.POINTER(C.c_uint)]
@@ -65,6 +66,27 @@ def plan(world, rank, rowptr, ind, col_global):
     return col_local[:nnz], hg[:k].copy(), ho[:k].copy(), hr[:k].copy()
 
 
+def build_sendmap(rank: int, halo_lists):
+    """Invert the halo lists: ``halo_lists[w] = (nl_w, halo_owner_w, halo_ridx_w)`` as
+    returned by :func:`plan` on rank ``w``.  Returns this rank's send map
+    (rows, dst_rank, dst_off): local row ``rows[s]`` goes to element ``dst_off[s]``
+    (= nl_w + halo position) of the vector on rank ``dst_rank[s]``."""
+    rows, dst_rank, dst_off = [], [], []
+    for w, (nl_w, ho, hr) in enumerate(halo_lists):
+        if w == rank:
+            continue
+        ho = np.asarray(ho)
+        hr = np.asarray(hr)
+        h = np.nonzero(ho == rank)[0]
+        rows.append(hr[h].astype(np.int32))
+        dst_rank.append(np.full(len(h), w, dtype=np.int32))
+        dst_off.append((nl_w + h).astype(np.int32))
+    if not rows:
+        z = np.zeros(0, dtype=np.int32)
+        return z, z.copy(), z.copy()
+    return np.concatenate(rows), np.concatenate(dst_rank), np.concatenate(dst_off)
+
+
 def init(rank: int, world: int, slot_elems: int, nslots: int = 6, group=None) -> None:
     """Create the symmetric heap and connect all ranks of the node (collective)."""
     import torch
@@ -92,7 +114,11 @@ def shutdown() -> None:
 class ShardedMatrix:
     """This rank's row slab of a CSR matrix (global column indices)."""
 
-    def __init__(self, rowptr, ind, col_global, val):
+    def __init__(self, rowptr, ind, col_global, val, group=None, sendmap=True):
+        """Collective when ``sendmap`` is true and the world has more than one rank: the
+        ranks exchange their halo lists (host metadata, through ``group``) so that each
+        one learns which of its rows the others need -- the send map of the push-model
+        halo exchange (psp_dist_set_sendmap)."""
         rowptr = np.ascontiguousarray(rowptr, dtype=np.int32)
         ind = np.ascontiguousarray(ind, dtype=np.int32)
         col_global = np.ascontiguousarray(col_global, dtype=np.int32)
@@ -104,6 +130,25 @@ class ShardedMatrix:
         nl, nh, mask = C.c_int(), C.c_int(), C.c_uint()
         P.check(P.lib.psp_dist_mat_info(self.ptr, C.byref(nl), C.byref(nh), C.byref(mask)))
         self.nl, self.nhalo, self.neighbour_mask = nl.value, nh.value, mask.value
+        self.nsend = 0
+        rank, world = C.c_int(), C.c_int()
+        P.check(P.lib.psp_dist_info(C.byref(rank), C.byref(world), None, None))
+        if sendmap and world.value > 1:
+            import torch.distributed as dist
+
+            _, _, ho, hr = plan(world.value, rank.value, rowptr, ind, col_global)
+            gathered = [None] * world.value
+            dist.all_gather_object(gathered, (self.nl, ho, hr), group=group)
+            rows, dst_rank, dst_off = build_sendmap(rank.value, gathered)
+            self.set_sendmap(rows, dst_rank, dst_off)
+
+    def set_sendmap(self, rows, dst_rank, dst_off):
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        dst_rank = np.ascontiguousarray(dst_rank, dtype=np.int32)
+        dst_off = np.ascontiguousarray(dst_off, dtype=np.int32)
+        P.check(P.lib.psp_dist_set_sendmap(self.ptr, len(rows), rows.ctypes.data_as(_ip),
+                                           dst_rank.ctypes.data_as(_ip), dst_off.ctypes.data_as(_ip)))
+        self.nsend = len(rows)
 
     def __del__(self):
         try:

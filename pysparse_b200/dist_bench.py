@@ -48,7 +48,7 @@ def run(args, bench):
     plane = args.grid * args.grid
     slot = nl + 2 * plane + 64
     D.init(rank, world, slot, nslots=4, group=ctl)
-    A = D.ShardedMatrix(rowptr, ind, col, val)
+    A = D.ShardedMatrix(rowptr, ind, col, val, group=ctl)
     K = P.Precon.jacobi(None, np.full(nl, 6.0))
     db = P.DeviceVector(nl, np.ones(nl))
     dx = P.DeviceVector(nl)

@@ -36,7 +36,7 @@ for kind, n, solver, rhs, jac in cases:
     val, col, ind = slab["csr"]
     nl = r1 - r0
     bfull = np.ones(N) if rhs == "ones" else np.random.default_rng(1).standard_normal(N)
-    A = D.ShardedMatrix(rowptr, ind, col, val)
+    A = D.ShardedMatrix(rowptr, ind, col, val, group=ctl)
     K = P.Precon.jacobi(None, np.full(nl, 6.0)) if jac else None
     db = P.DeviceVector(nl, bfull[r0:r1]); dx = P.DeviceVector(nl, np.zeros(nl))
     res = D.solve(solver, A, db, dx, tol, 2000, K, DIM)
@@ -64,6 +64,14 @@ for kind, n, solver, rhs, jac in cases:
     if res2 != res:
         print(f"rank {rank}: repeated solve differs: {res} vs {res2}", flush=True)
         ok = False
+    # pull-model halo exchange on the same handles, then push again
+    for push in (0, 1):
+        P.set_option("dist_push", push)
+        dx.fill(0.0)
+        res3 = D.solve(solver, A, db, dx, tol, 2000, K, DIM)
+        if res3 != res:
+            print(f"rank {rank}: dist_push={push} solve differs: {res} vs {res3}", flush=True)
+            ok = False
     del A
 flags = [None] * world
 dist.all_gather_object(flags, ok, group=ctl)

@@ -63,7 +63,7 @@ if "c3" in want:
     rowptr = D.row_partition(N, world, align=n * n)
     r0, r1 = int(rowptr[rank]), int(rowptr[rank + 1])
     slab = g.poisson3d(n, want_sss=False, rows=(r0, r1))
-    A = D.ShardedMatrix(rowptr, slab["csr"][2], slab["csr"][1], slab["csr"][0])
+    A = D.ShardedMatrix(rowptr, slab["csr"][2], slab["csr"][1], slab["csr"][0], group=ctl)
     nl = r1 - r0
     K = P.Precon.jacobi(None, np.full(nl, 6.0))
     db = P.DeviceVector(nl, np.ones(nl)); dx = P.DeviceVector(nl)
@@ -78,7 +78,7 @@ if "c4" in want:
     rowptr = D.row_partition(N, world, align=n * n)
     r0, r1 = int(rowptr[rank]), int(rowptr[rank + 1])
     slab = g.convdiff3d(n, rows=(r0, r1))
-    A = D.ShardedMatrix(rowptr, slab["csr"][2], slab["csr"][1], slab["csr"][0])
+    A = D.ShardedMatrix(rowptr, slab["csr"][2], slab["csr"][1], slab["csr"][0], group=ctl)
     nl = r1 - r0
     K = P.Precon.jacobi(None, np.full(nl, 6.0))
     bfull = np.random.default_rng(1).standard_normal(N)

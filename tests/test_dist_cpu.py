@@ -66,6 +66,38 @@ def test_plan_poisson3d_halo_is_one_plane_per_neighbour(native):
         assert len(hg) == len(nb) * n * n and sorted(set(ho.tolist())) == nb
 
 
+@pytest.mark.parametrize("world", [2, 3, 5])
+def test_sendmap_push_fills_every_halo_entry(native, world):
+    """The send map (push model) is the exact inverse of the halo lists: pushing with it
+    writes every rank's halo, each entry once, with the value the pull model would fetch."""
+    from pysparse_b200 import dist as D
+    mat = gallery.powerlaw(300, mean_nnz=6, seed=5, max_len=40)
+    val, col, ind = mat["csr"]
+    n = mat["n"]
+    rowptr = D.row_partition(n, world)
+    x = np.random.default_rng(1).standard_normal(n)
+    lists, halos = [], []
+    for r in range(world):
+        r0, r1 = rowptr[r], rowptr[r + 1]
+        k0, k1 = ind[r0], ind[r1]
+        _, hg, ho, hr = D.plan(world, r, rowptr, (ind[r0:r1 + 1] - k0).astype(np.int32), col[k0:k1])
+        lists.append((int(r1 - r0), ho, hr))
+        halos.append(hg)
+    vecs = [np.concatenate([x[rowptr[r]:rowptr[r + 1]], np.full(len(halos[r]), np.nan)]) for r in range(world)]
+    hits = [np.zeros(len(v), dtype=int) for v in vecs]
+    for r in range(world):
+        rows, dst_rank, dst_off = D.build_sendmap(r, lists)
+        assert rows.dtype == dst_rank.dtype == dst_off.dtype == np.int32
+        assert not np.any(dst_rank == r)
+        for s in range(len(rows)):
+            vecs[dst_rank[s]][dst_off[s]] = vecs[r][rows[s]]
+            hits[dst_rank[s]][dst_off[s]] += 1
+    for r in range(world):
+        nl = lists[r][0]
+        assert np.all(hits[r][:nl] == 0) and np.all(hits[r][nl:] == 1)
+        assert np.array_equal(vecs[r][nl:], x[halos[r]])
+
+
 WORKER = r'''
 import os, sys
 import numpy as np
