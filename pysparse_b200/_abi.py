@@ -16,7 +16,8 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libpsp_b200.so")
+#: PSP_B200_LIB selects another build of the same library (A/B timing of kernel variants)
+LIB_PATH = os.environ.get("PSP_B200_LIB") or os.path.join(_PKG, "libpsp_b200.so")
 
 #: every symbol include/psp_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [

@@ -55,7 +55,10 @@ constexpr int kMailRing = 4;
 struct DistMail {                       // one all-reduce contribution
   double val[kRedSlots + 1];            // sums, then the max
   unsigned long long seq;               // written last (release); reduction sequence number
-  unsigned long long pad[6];
+  // flag-in-data copy used by the persistent kernels: word 2k / 2k+1 = low / high half of
+  // value k in the low 32 bits, the low 32 bits of the sequence number in the high ones --
+  // every 8-byte word validates itself, so no release fence and a single NVLink trip
+  unsigned long long ll[8];
 };
 
 struct DistCtl {                        // lives in each rank's IPC-shared control block

@@ -29,16 +29,30 @@ namespace cg = cooperative_groups;
 
 namespace psp {
 
-constexpr int kPersistStages = 2;
+// tuning constants (overridable for A/B builds: PSP_NVCC_EXTRA="-DPSP_PERSIST_CTAS=3 ...")
+#ifndef PSP_PERSIST_STAGES
+#define PSP_PERSIST_STAGES 2
+#endif
+#ifndef PSP_PERSIST_CTAS
+#define PSP_PERSIST_CTAS 4
+#endif
+#ifndef PSP_VEC_UNROLL
+#define PSP_VEC_UNROLL 1
+#endif
+constexpr int kPersistStages = PSP_PERSIST_STAGES;   // TMA ring depth
+constexpr int kPersistCtas = PSP_PERSIST_CTAS;       // CTAs per SM the register budget is sized for
+constexpr int kVecUnroll = PSP_VEC_UNROLL;           // elements per thread and trip in the vector phases
+struct PersistSync;
 
 struct PcgArgs {
   MatView A;
   int n;                        // local rows
   const double *b;
-  double *x, *r, *p, *q;
+  double *x, *r, *p, *p2, *q;    // p, p2: the two buffers of the search direction
   const double *dinv;           // nullptr: identity preconditioner
   State *S;
   double *partials;             // 2 x (kRedSlots + 1) x kMaxGrid, double-buffered
+  PersistSync *sync;
   int l2_stream;
   int dist_debug;               // timing diagnostics (see Ctx::dist_debug)
   // multi-GPU
@@ -51,87 +65,193 @@ struct PcgArgs {
   unsigned sendmask;
 };
 
+struct PersistSync {            // global scratch of the all-reduce / barrier (zeroed before each launch)
+  unsigned ticket, pad;
+  unsigned long long flag;      // generation of the last completed all-reduce
+  double result[2][kRedSlots + 1];
+};
+
 struct PersistCtx {
   State *sS;                    // shared-memory copy of the solver state
   double *tot;                  // shared: kRedSlots + 1 totals
-  double *red_sh;               // shared: 8 doubles
+  double *red_sh;               // shared: 8 * (kRedSlots + 1) doubles
   double *partials;
+  PersistSync *sync;
   DistDev *dd;
-  unsigned long long seq, pubs, pulls;
+  unsigned long long seq, pubs, pulls, gen;
   int parity;
   int debug;
+#ifdef PSP_PERSIST_PROF
+  long long prof[16], t_last;
+#endif
 };
 
-// Grid-wide deterministic reduction; on return tot[0..NS) (and tot[kRedSlots] for the
-// max) are valid in every thread of every CTA.
+// diagnostic build (PSP_NVCC_EXTRA=-DPSP_PERSIST_PROF): CTA 0 / thread 0 accumulates the SM
+// cycles it spends in each segment of the iteration and prints them when the kernel ends
+#ifdef PSP_PERSIST_PROF
+#define PROF_T(c, k)                                                     \
+  do {                                                                   \
+    if (blockIdx.x == 0 && threadIdx.x == 0) {                           \
+      const long long t_ = clock64();                                    \
+      (c).prof[k] += t_ - (c).t_last;                                    \
+      (c).t_last = t_;                                                   \
+    }                                                                    \
+  } while (0)
+#else
+#define PROF_T(c, k)
+#endif
+
+// Sums (and one max) of up to kRedSlots + 1 per-thread values over the CTA in ONE pass:
+// warp shuffles, one shared-memory exchange, two CTA barriers.  Result in thread 0.
+// sh: 8 * (kRedSlots + 1) doubles.  Fixed order, so every CTA / rank / run agrees.
 template <int NS, bool HASMAX>
-__device__ __forceinline__ void grid_allreduce(cg::grid_group &grid, PersistCtx &c, const double *acc, double mx) {
-  double *buf = c.partials + (size_t)c.parity * (kRedSlots + 1) * kMaxGrid;
-  c.parity ^= 1;
+__device__ __forceinline__ void block_reduce_multi(double *v, double &mx, double *sh) {
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
 #pragma unroll
-  for (int s = 0; s < NS; s++) {
-    double v = block_sum(acc[s], c.red_sh);
-    if (threadIdx.x == 0) buf[s * kMaxGrid + blockIdx.x] = v;
-  }
-  if (HASMAX) {
-    double v = block_max(mx, c.red_sh);
-    if (threadIdx.x == 0) buf[kRedSlots * kMaxGrid + blockIdx.x] = v;
-  }
-  grid.sync();
-  const volatile double *vp = buf;
+  for (int s = 0; s < NS; s++) v[s] = warp_sum(v[s]);
+  if (HASMAX) mx = warp_max(mx);
+  __syncthreads();
+  if (l == 0) {
 #pragma unroll
-  for (int s = 0; s < NS; s++) {
-    double a = 0.0;
-    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) a += vp[s * kMaxGrid + i];
-    a = block_sum(a, c.red_sh);
-    if (threadIdx.x == 0) c.tot[s] = a;
-  }
-  if (HASMAX) {
-    double a = 0.0;
-    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) a = fmax(a, vp[kRedSlots * kMaxGrid + i]);
-    a = block_max(a, c.red_sh);
-    if (threadIdx.x == 0) c.tot[kRedSlots] = a;
+    for (int s = 0; s < NS; s++) sh[s * 8 + w] = v[s];
+    if (HASMAX) sh[kRedSlots * 8 + w] = mx;
   }
   __syncthreads();
-  if (c.dd && c.debug < 2) {
-    // cross-GPU: CTA 0 pushes this rank's totals to every peer's mailbox; every CTA
-    // reads the W contributions from the LOCAL mailbox and adds them in rank order
-    __shared__ double box[kMaxRanks][kRedSlots + 1];
-    DistDev *dd = c.dd;
-    const int W = dd->world, me = dd->rank;
-    const unsigned long long seq = ++c.seq;
-    const int slot = (int)(seq % kMailRing);
-    if ((int)threadIdx.x < W) {
-      const int w = threadIdx.x;
-      if (blockIdx.x == 0) {
-        DistMail *dst = &dd->ctl[w]->mail[slot][me];
+  if (w == 0) {
 #pragma unroll
-        for (int s = 0; s < NS; s++) st_relaxed_sys_f64(&dst->val[s], c.tot[s]);
-        if (HASMAX) st_relaxed_sys_f64(&dst->val[kRedSlots], c.tot[kRedSlots]);
-        st_release_sys(&dst->seq, seq);
-      }
-      const DistMail *src = &dd->ctl[me]->mail[slot][w];
-      while (ld_acquire_sys(&src->seq) != seq) { }
+    for (int s = 0; s < NS; s++) {
+      double r = (l < 8) ? sh[s * 8 + l] : 0.0;
 #pragma unroll
-      for (int s = 0; s < NS; s++) box[w][s] = ld_relaxed_sys_f64(&src->val[s]);
-      if (HASMAX) box[w][kRedSlots] = ld_relaxed_sys_f64(&src->val[kRedSlots]);
+      for (int o = 4; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+      v[s] = r;
     }
-    __syncthreads();
+    if (HASMAX) {
+      double r = (l < 8) ? sh[kRedSlots * 8 + l] : 0.0;
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) r = fmax(r, __shfl_xor_sync(0xffffffffu, r, o));
+      mx = r;
+    }
+  }
+}
+
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_release_gpu_u64(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Grid-wide deterministic all-reduce AND grid barrier in one: every CTA deposits its
+// partial sums and draws a ticket; the CTA that draws the last one adds the partials up
+// in a fixed order (so the result does not depend on which CTA that is), does the
+// cross-GPU exchange through the peer mailboxes when the solve is sharded, publishes the
+// totals and releases the others, which have been spinning on one flag.  Only one CTA
+// reads the partials and only one polls the mailboxes.  On return tot[0..NS) (and
+// tot[kRedSlots] for the max) are valid in every thread of every CTA, and all global
+// writes made before the call are visible grid-wide.
+template <int NS, bool HASMAX>
+__device__ __forceinline__ void grid_allreduce(PersistCtx &c, const double *acc, double mx) {
+  __shared__ int is_last;
+  __shared__ unsigned box[kMaxRanks][8];
+  double *buf = c.partials + (size_t)c.parity * (kRedSlots + 1) * kMaxGrid;
+  double *res = c.sync->result[c.parity];
+  c.parity ^= 1;
+  const unsigned long long gen = ++c.gen;
+  const bool xgpu = c.dd && c.debug < 2;
+  const unsigned long long seq = xgpu ? ++c.seq : c.seq;      // every CTA keeps count
+  double v[NS > 0 ? NS : 1];
+#pragma unroll
+  for (int s = 0; s < NS; s++) v[s] = acc[s];
+  block_reduce_multi<NS, HASMAX>(v, mx, c.red_sh);
+  PROF_T(c, 8);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < NS; s++) buf[s * kMaxGrid + blockIdx.x] = v[s];
+    if (HASMAX) buf[kRedSlots * kMaxGrid + blockIdx.x] = mx;
+    __threadfence();
+    const unsigned t = atomicAdd(&c.sync->ticket, 1u);
+    __threadfence();
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    double a[NS > 0 ? NS : 1], m = 0.0;
+#pragma unroll
+    for (int s = 0; s < NS; s++) a[s] = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
+#pragma unroll
+      for (int s = 0; s < NS; s++) a[s] += __ldcg(buf + s * kMaxGrid + i);
+      if (HASMAX) m = fmax(m, __ldcg(buf + kRedSlots * kMaxGrid + i));
+    }
+    block_reduce_multi<NS, HASMAX>(a, m, c.red_sh);
     if (threadIdx.x == 0) {
 #pragma unroll
-      for (int s = 0; s < NS; s++) {
-        double a = 0.0;
-        for (int w = 0; w < W; w++) a += box[w][s];
-        c.tot[s] = a;
+      for (int s = 0; s < NS; s++) c.tot[s] = a[s];
+      if (HASMAX) c.tot[kRedSlots] = m;
+    }
+    if (xgpu) {
+      // cross-GPU, one NVLink trip: thread (w, j) stores word j of this rank's totals into
+      // rank w's mailbox (payload + sequence tag in one 8-byte word, see DistMail::ll) and
+      // spins on the LOCAL mailbox until rank w's word j of the same sequence number is
+      // there; thread 0 then adds the W contributions in rank order.
+      constexpr int NV = NS + (HASMAX ? 1 : 0);
+      static_assert(2 * NV <= 8, "DistMail::ll holds four values");
+      __syncthreads();
+      DistDev *dd = c.dd;
+      const int W = dd->world, me = dd->rank;
+      const int slot = (int)(seq % kMailRing);
+      const unsigned tag = (unsigned)seq;
+      if ((int)threadIdx.x < W * 2 * NV) {
+        const int w = threadIdx.x / (2 * NV), j = threadIdx.x % (2 * NV);
+        const int k = j >> 1;
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(k < NS ? c.tot[k] : c.tot[kRedSlots]);
+        const unsigned half = (j & 1) ? (unsigned)(bits >> 32) : (unsigned)bits;
+        st_relaxed_sys_u64(&dd->ctl[w]->mail[slot][me].ll[j], ((unsigned long long)tag << 32) | half);
+        const unsigned long long *src = &dd->ctl[me]->mail[slot][w].ll[j];
+        unsigned long long got;
+        do { got = ld_relaxed_sys_u64(src); } while ((unsigned)(got >> 32) != tag);
+        box[w][j] = (unsigned)got;
       }
-      if (HASMAX) {
-        double a = 0.0;
-        for (int w = 0; w < W; w++) a = fmax(a, box[w][kRedSlots]);
-        c.tot[kRedSlots] = a;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+          double t = 0.0;
+          for (int w = 0; w < W; w++) {
+            const double v = __longlong_as_double((long long)(((unsigned long long)box[w][2 * k + 1] << 32) | box[w][2 * k]));
+            t = (k < NS) ? t + v : fmax(t, v);
+          }
+          c.tot[k < NS ? k : kRedSlots] = t;
+        }
       }
     }
-    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int s = 0; s < NS; s++) res[s] = c.tot[s];
+      if (HASMAX) res[kRedSlots] = c.tot[kRedSlots];
+      c.sync->ticket = 0u;               // nobody draws again before the flag moves
+      __threadfence();
+      st_release_gpu_u64(&c.sync->flag, gen);
+    }
+  } else if (threadIdx.x == 0) {
+    while (ld_relaxed_gpu_u64(&c.sync->flag) < gen) { }
+    __threadfence();
+#pragma unroll
+    for (int s = 0; s < NS; s++) c.tot[s] = __ldcg(res + s);
+    if (HASMAX) c.tot[kRedSlots] = __ldcg(res + kRedSlots);
   }
+  __syncthreads();
+  PROF_T(c, 9);
 }
 
 // thread 0 of every CTA advances its copy of the state; all copies stay identical
@@ -170,33 +290,32 @@ __device__ __forceinline__ void publish_and_pull(cg::grid_group &grid, PersistCt
   grid.sync();
 }
 
-// Push model (needs the send map, psp_dist_set_sendmap): called after the grid barrier
-// that completes `vec`.  Every thread stores its share of the boundary entries straight
-// into the neighbours' heaps (posted NVLink stores, nobody waits for them); the CTA that
-// finishes last raises the "arrived" counters in the neighbours' control blocks; then the
-// CTA waits -- on LOCAL memory -- until its own neighbours' entries have arrived.  No
-// remote loads, no second grid barrier.  The wait (halo_wait) is deferred to the first
-// row block that reads a halo column, so the transfer overlaps the interior blocks.
-__device__ __forceinline__ void halo_push(PersistCtx &c, const PcgArgs &a, const double *vec, size_t slot_off) {
+// Push model (needs the send map, psp_dist_set_sendmap).  The search direction is double-
+// buffered (p_cur is read, p_new is written), so the boundary entries of p_new can be
+// computed and stored straight into the neighbours' heaps at the START of the p-update
+// phase (posted NVLink stores, nobody waits for them); by the time the phase ends they
+// have long been acknowledged, so the system-scope fence before the grid barrier is
+// cheap.  After the barrier one CTA raises the "arrived" counters in the neighbours'
+// control blocks.  The wait for the neighbours' entries (halo_wait, on LOCAL memory) is
+// deferred to the first row block that reads a halo column, so the whole exchange
+// overlaps the p update and the interior blocks.  No remote loads, no extra barrier.
+__device__ __forceinline__ void halo_fence(const PersistCtx &c, const PcgArgs &a) {
+  if (c.debug >= 1) return;
+  if ((long)blockIdx.x * blockDim.x < a.nsend) {       // this CTA issued remote stores
+    __syncthreads();
+    if (threadIdx.x == 0) __threadfence_system();
+  }
+}
+
+// after the grid barrier that follows halo_fence()
+__device__ __forceinline__ void halo_signal(PersistCtx &c, const PcgArgs &a) {
   DistDev *dd = c.dd;
-  const int me = dd->rank;
   c.pubs += 1;
   c.pulls += 1;
   if (c.debug >= 1) return;
-  const int stride = gridDim.x * blockDim.x;
-  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < a.nsend; s += stride)
-    st_relaxed_sys_f64(dd->heap[a.send_rank[s]] + slot_off + a.send_off[s], vec[a.send_row[s]]);
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence_system();
-    const unsigned t = atomicAdd(&dd->push_ticket, 1u);
-    if (t == gridDim.x - 1) {
-      dd->push_ticket = 0u;
-      __threadfence_system();
-      for (int w = 0; w < dd->world; w++)
-        if ((a.sendmask >> w) & 1u) st_release_sys(&dd->ctl[w]->arrived[me], c.pubs);
-    }
-  }
+  const int w = threadIdx.x;
+  if (blockIdx.x == 0 && w < dd->world && ((a.sendmask >> w) & 1u))
+    st_release_sys(&dd->ctl[w]->arrived[dd->rank], c.pubs);
 }
 
 __device__ __forceinline__ void halo_wait(PersistCtx &c, const PcgArgs &a) {
@@ -210,10 +329,10 @@ __device__ __forceinline__ void halo_wait(PersistCtx &c, const PcgArgs &a) {
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(kThreads, 4) k_pcg_persist(PcgArgs a, size_t p_slot_off) {
+__global__ void __launch_bounds__(kThreads, kPersistCtas) k_pcg_persist(PcgArgs a, size_t p_slot_off, size_t p2_slot_off) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t full[kPersistStages];
-  __shared__ double red_sh[8];
+  __shared__ double red_sh[8 * (kRedSlots + 1)];
   __shared__ double tot[kRedSlots + 1];
   __shared__ State sS;
   cg::grid_group grid = cg::this_grid();
@@ -225,11 +344,13 @@ __global__ void __launch_bounds__(kThreads, 4) k_pcg_persist(PcgArgs a, size_t p
   if (tid == 0) sS = *a.S;
   __syncthreads();
   PersistCtx c;
-  c.sS = &sS; c.tot = tot; c.red_sh = red_sh; c.partials = a.partials; c.parity = 0;
+  c.sS = &sS; c.tot = tot; c.red_sh = red_sh; c.partials = a.partials; c.sync = a.sync; c.parity = 0; c.gen = 0;
   c.dd = sS.dist;
   c.debug = a.dist_debug;
   c.seq = c.pubs = c.pulls = 0;
   if (c.dd) { c.seq = c.dd->red_seq; c.pubs = c.dd->pubs_done; c.pulls = c.dd->pulls_done; }
+  const bool push = c.dd && a.push;
+  const bool do_push = push && c.debug < 1;
 
   Ring<kPersistStages> ring;
   ring.init(smem, full, a.l2_stream != 0);
@@ -239,20 +360,28 @@ __global__ void __launch_bounds__(kThreads, 4) k_pcg_persist(PcgArgs a, size_t p
   {
     double acc[1] = {0.0};
     for (long i = g0; i < n; i += gstride) { double t = a.b[i]; acc[0] += t * t; }
-    grid_allreduce<1, false>(grid, c, acc, 0.0);
+    grid_allreduce<1, false>(c, acc, 0.0);
     epilogue<1, false>(c, EPI_PCG_NORMB);
   }
+  // the two buffers of the search direction (sharded: two slots of the symmetric heap)
+  // (only the push model needs two: without it the update is done in place)
+  double *p_cur = a.p, *p_new = push ? a.p2 : a.p;
+  size_t off_cur = p_slot_off, off_new = push ? p2_slot_off : p_slot_off;
   // ---- r = b - A x0  (pcg.c:72-89)
   const double *xin = a.x;
   if (c.dd) {
-    for (long i = g0; i < n; i += gstride) a.p[i] = a.x[i];
+    if (do_push)
+      for (long s = g0; s < a.nsend; s += gstride)
+        st_relaxed_sys_f64(c.dd->heap[a.send_rank[s]] + off_cur + a.send_off[s], a.x[a.send_row[s]]);
+    for (long i = g0; i < n; i += gstride) p_cur[i] = a.x[i];
+    if (push) halo_fence(c, a);
     grid.sync();
-    if (a.push) halo_push(c, a, a.p, p_slot_off);
-    else publish_and_pull(grid, c, a, a.p, p_slot_off);
-    xin = a.p;
+    if (push) halo_signal(c, a);
+    else publish_and_pull(grid, c, a, p_cur, off_cur);
+    xin = p_cur;
   }
   ring.template pass<false>(a.A, xin, red_sh, [&](int r, double sum) { a.r[r] = sum; },
-                            [&] { if (a.push) halo_wait(c, a); });
+                            [&] { if (push) halo_wait(c, a); });
   ring.prefetch(a.A);
   grid.sync();
   {
@@ -266,56 +395,122 @@ __global__ void __launch_bounds__(kThreads, 4) k_pcg_persist(PcgArgs a, size_t p
       double z = a.dinv ? t * a.dinv[i] : t;
       acc[1] += t * z;
     }
-    grid_allreduce<2, false>(grid, c, acc, 0.0);
+    grid_allreduce<2, false>(c, acc, 0.0);
     epilogue<2, false>(c, EPI_PCG_RESID0_J);
   }
 
   // ---- iterations  (pcg.c:91-165)
+#ifdef PSP_PERSIST_PROF
+  for (int k = 0; k < 16; k++) c.prof[k] = 0;
+  c.t_last = clock64();
+#endif
   while (!sS.done) {
-    {                                   // p = z + beta p   (first: p = z)
+    {                                   // p_new = z + beta p_cur   (first: p_new = z)
       const double beta = sS.v[V_BETA];
       const bool first = (sS.it == 1);
-      for (long i = g0; i < n; i += gstride) {
-        double ri = a.r[i];
-        double zi = a.dinv ? ri * a.dinv[i] : ri;
-        a.p[i] = first ? zi : zi + beta * a.p[i];
+      if (do_push) {
+        // boundary entries first, straight to the neighbours (same arithmetic as below)
+        for (long s = g0; s < a.nsend; s += gstride) {
+          const int row = a.send_row[s];
+          const double ri = a.r[row];
+          const double zi = a.dinv ? ri * a.dinv[row] : ri;
+          const double pv = first ? zi : zi + beta * p_cur[row];
+          st_relaxed_sys_f64(c.dd->heap[a.send_rank[s]] + off_new + a.send_off[s], pv);
+        }
+      }
+      for (long i0 = g0; i0 < n; i0 += kVecUnroll * gstride) {
+        double ri[kVecUnroll], di[kVecUnroll], pi[kVecUnroll];
+#pragma unroll
+        for (int u = 0; u < kVecUnroll; u++) {
+          const long i = i0 + u * gstride;
+          const bool ok = i < n;
+          ri[u] = ok ? a.r[i] : 0.0;
+          di[u] = (ok && a.dinv) ? a.dinv[i] : 1.0;
+          pi[u] = (ok && !first) ? p_cur[i] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < kVecUnroll; u++) {
+          const long i = i0 + u * gstride;
+          if (i < n) {
+            const double zi = a.dinv ? ri[u] * di[u] : ri[u];
+            p_new[i] = first ? zi : zi + beta * pi[u];
+          }
+        }
       }
     }
+    PROF_T(c, 0);
+    if (push) halo_fence(c, a);
     grid.sync();
+    PROF_T(c, 1);
     if (c.dd) {
-      if (a.push) halo_push(c, a, a.p, p_slot_off);
-      else publish_and_pull(grid, c, a, a.p, p_slot_off);
+      if (push) halo_signal(c, a);
+      else publish_and_pull(grid, c, a, p_new, off_new);
     }
+    PROF_T(c, 2);
     {                                   // q = A p ; pq = p.q
       double acc[1] = {0.0};
-      ring.template pass<false>(a.A, a.p, red_sh, [&](int r, double sum) { a.q[r] = sum; acc[0] += a.p[r] * sum; },
-                                [&] { if (a.push) halo_wait(c, a); });
+      ring.template pass<false>(a.A, p_new, red_sh, [&](int r, double sum) { a.q[r] = sum; acc[0] += p_new[r] * sum; },
+                                [&] { if (push) halo_wait(c, a); });
       ring.prefetch(a.A);
-      grid_allreduce<1, false>(grid, c, acc, 0.0);
+      PROF_T(c, 3);
+      grid_allreduce<1, false>(c, acc, 0.0);
+      PROF_T(c, 4);
       epilogue<1, false>(c, EPI_PCG_PQ);
+      PROF_T(c, 5);
     }
     if (sS.done) break;
     {                                   // stagnation scan, x += alpha p, r -= alpha q, |r|^2, r.K^-1 r
       const double alpha = sS.v[V_ALPHA];
       const bool scan = (sS.stag == 0);
       double acc[2] = {0.0, 0.0}, mx = 0.0;
-      for (long i = g0; i < n; i += gstride) {
-        double xi = a.x[i], pi = a.p[i];
-        if (scan) {
-          if (xi != 0.0) mx = fmax(mx, fabs(alpha * pi / xi));
-          else if (pi != 0.0) mx = fmax(mx, 1.0);
+      for (long i0 = g0; i0 < n; i0 += kVecUnroll * gstride) {
+        double xv[kVecUnroll], pv[kVecUnroll], rv[kVecUnroll], qv[kVecUnroll], dv[kVecUnroll];
+#pragma unroll
+        for (int u = 0; u < kVecUnroll; u++) {
+          const long i = i0 + u * gstride;
+          const bool ok = i < n;
+          xv[u] = ok ? a.x[i] : 0.0;
+          pv[u] = ok ? p_new[i] : 0.0;
+          rv[u] = ok ? a.r[i] : 0.0;
+          qv[u] = ok ? a.q[i] : 0.0;
+          dv[u] = (ok && a.dinv) ? a.dinv[i] : 1.0;
         }
-        a.x[i] = xi + alpha * pi;
-        double t = a.r[i] + (-alpha) * a.q[i];
-        a.r[i] = t;
-        acc[0] += t * t;
-        double z = a.dinv ? t * a.dinv[i] : t;
-        acc[1] += t * z;
+#pragma unroll
+        for (int u = 0; u < kVecUnroll; u++) {
+          const long i = i0 + u * gstride;
+          if (i < n) {
+            const double xi = xv[u], pi = pv[u];
+            if (scan) {
+              if (xi != 0.0) mx = fmax(mx, fabs(alpha * pi / xi));
+              else if (pi != 0.0) mx = fmax(mx, 1.0);
+            }
+            a.x[i] = xi + alpha * pi;
+            const double t = rv[u] + (-alpha) * qv[u];
+            a.r[i] = t;
+            acc[0] += t * t;
+            const double z = a.dinv ? t * dv[u] : t;
+            acc[1] += t * z;
+          }
+        }
       }
-      grid_allreduce<2, true>(grid, c, acc, mx);
+      PROF_T(c, 6);
+      grid_allreduce<2, true>(c, acc, mx);
+      PROF_T(c, 4);
       epilogue<2, true>(c, EPI_PCG_UPDATE_J);
+      PROF_T(c, 7);
     }
+    { double *t = p_cur; p_cur = p_new; p_new = t; }
+    { const size_t t = off_cur; off_cur = off_new; off_new = t; }
   }
+#ifdef PSP_PERSIST_PROF
+  if (blockIdx.x == 0 && tid == 0 && sS.it > 100) {
+    const double k = 1.0 / (double)sS.it;
+    printf("persist prof (cycles/iter, it=%d): p-update %.0f | sync %.0f | halo push %.0f | pass %.0f | "
+           "allreduce[partials %.0f gridsync %.0f sum %.0f xgpu %.0f] | epi pq %.0f | update %.0f | epi upd %.0f\n",
+           sS.it, c.prof[0] * k, c.prof[1] * k, c.prof[2] * k, c.prof[3] * k, c.prof[8] * k, c.prof[9] * k, c.prof[10] * k,
+           c.prof[4] * k, c.prof[5] * k, c.prof[6] * k, c.prof[7] * k);
+  }
+#endif
 
   ring.drain(a.A);
   if (blockIdx.x == 0 && tid == 0) {
@@ -325,10 +520,11 @@ __global__ void __launch_bounds__(kThreads, 4) k_pcg_persist(PcgArgs a, size_t p
 }
 
 static double *g_partials2 = nullptr;
+static PersistSync *g_sync = nullptr;
 
 // Host entry: returns PSP_OK after ENQUEUEING the solve (one cooperative launch).
-int pcg_persist_launch(const psp_mat *M, int n, const double *b, double *x, double *r, double *p, double *q,
-                       const double *dinv, DistMat *dm) {
+int pcg_persist_launch(const psp_mat *M, int n, const double *b, double *x, double *r, double *p, double *p2,
+                       double *q, const double *dinv, DistMat *dm) {
   Ctx &c = ctx();
   static int resident = 0;
   const int smem_bytes = kPersistStages * kStageBytes;
@@ -341,12 +537,14 @@ int pcg_persist_launch(const psp_mat *M, int n, const double *b, double *x, doub
     if (resident > kMaxGrid) resident = kMaxGrid;
   }
   if (!g_partials2) PSP_CUDA(cudaMalloc((void **)&g_partials2, sizeof(double) * 2 * (kRedSlots + 1) * kMaxGrid));
+  if (!g_sync) PSP_CUDA(cudaMalloc((void **)&g_sync, sizeof(PersistSync)));
+  PSP_CUDA(cudaMemsetAsync(g_sync, 0, sizeof(PersistSync), c.stream));
   PcgArgs a;
   a.A.ind = M->d_ind; a.A.col = M->d_col; a.A.val = M->d_val; a.A.nb = M->nb;
   a.A.blk = reinterpret_cast<const int4 *>(M->d_blk);
   a.A.nint = M->nint;
-  a.n = n; a.b = b; a.x = x; a.r = r; a.p = p; a.q = q; a.dinv = dinv;
-  a.S = c.state; a.partials = g_partials2; a.l2_stream = l2_stream_for(n); a.dist_debug = (int)c.dist_debug;
+  a.n = n; a.b = b; a.x = x; a.r = r; a.p = p; a.p2 = p2; a.q = q; a.dinv = dinv;
+  a.S = c.state; a.partials = g_partials2; a.sync = g_sync; a.l2_stream = l2_stream_for(n); a.dist_debug = (int)c.dist_debug;
   a.halo_owner = dm ? dm->d_owner : nullptr; a.halo_ridx = dm ? dm->d_ridx : nullptr;
   a.nhalo = dm ? dm->nhalo : 0; a.nbmask = dm ? dm->nbmask : 0u;
   a.push = (dm && dm->has_sendmap && c.dist_push) ? 1 : 0;
@@ -354,11 +552,12 @@ int pcg_persist_launch(const psp_mat *M, int n, const double *b, double *x, doub
   a.send_row = dm ? dm->d_send_row : nullptr; a.send_rank = dm ? dm->d_send_rank : nullptr;
   a.send_off = dm ? dm->d_send_off : nullptr;
   size_t p_slot_off = dm ? (size_t)(p - dist().heap) : 0;
+  size_t p2_slot_off = dm ? (size_t)(p2 - dist().heap) : 0;
   // enough CTAs for the vector phases and the row blocks, never more than are co-resident
   long long want = (n + kThreads - 1) / kThreads;
   if (M->nb > want) want = M->nb;
   int grid = (int)(want < resident ? (want > 0 ? want : 1) : resident);
-  void *args[] = {&a, &p_slot_off};
+  void *args[] = {&a, &p_slot_off, &p2_slot_off};
   PSP_CUDA(cudaLaunchCooperativeKernel((const void *)k_pcg_persist, dim3(grid), dim3(kThreads), args, smem_bytes, c.stream));
   c.launches++;
   return PSP_OK;

@@ -16,7 +16,7 @@
 namespace psp {
 
 int prec_apply_dev(psp_prec *K, const double *dx, double *dy, State *gateS);   // psp_precon.cu
-int pcg_persist_launch(const psp_mat *M, int n, const double *b, double *x, double *r, double *p, double *q,
+int pcg_persist_launch(const psp_mat *M, int n, const double *b, double *x, double *r, double *p, double *p2, double *q,
                        const double *dinv, DistMat *dm);                        // psp_persist.cu
 
 // ------------------------------------------------------------------ generic functors
@@ -238,13 +238,14 @@ static int solve_pcg(Solve &s, const double *b, double *x, double *work) {
   const int pub = s.dm ? kPublish : 0;     // multi-GPU: p is read by the neighbours
   {
     // single-launch path: the whole solve in one persistent cooperative kernel
-    // (psp_persist.cu).  pcg_persist: 1 always, 0 never, -1 (default) when the slab is
-    // small enough that launch / barrier latency matters (<= 2^22 rows) or sharded.
+    // (psp_persist.cu).  pcg_persist: 0 never, anything else (default -1) whenever the
+    // operator and the preconditioner are native (it wins at every size measured:
+    // 256^3 563 vs 581 us/iteration, 128^3 77 vs 86, 100^2 16 vs 23).
     Ctx &c = ctx();
     const psp_mat *M = s.dm ? s.dm->local : s.A.mat;
     const bool eligible = M && s.fusedK;
-    const bool choose = c.pcg_persist == 1 || (c.pcg_persist < 0 && (s.dm || n <= (1L << 22)));
-    if (eligible && choose) return pcg_persist_launch(M, (int)n, b, x, r, p, q, s.dinv, s.dm);
+    const bool choose = c.pcg_persist != 0;
+    if (eligible && choose) return pcg_persist_launch(M, (int)n, b, x, r, p, z, q, s.dinv, s.dm);   // z: second p buffer
   }
   PSP_TRY(launch_map(FNormSq{b}, n, EPI_PCG_NORMB));
   if (s.dm) {
