@@ -64,7 +64,6 @@ struct DistMail {                       // one all-reduce contribution
 struct DistCtl {                        // lives in each rank's IPC-shared control block
   unsigned long long pub;               // number of vector publications completed by this rank
   unsigned long long pad[7];
-  unsigned long long arrived[kMaxRanks];  // push model: arrived[w] = halo pushes rank w has completed into THIS rank
   DistMail mail[kMailRing][kMaxRanks];  // mail[seq % ring][source rank]
 };
 
@@ -75,7 +74,10 @@ struct DistDev {                        // device-resident descriptor (private t
   unsigned long long red_seq;           // reductions performed so far (identical on all ranks)
   unsigned long long pubs_done;         // publications performed by this rank
   unsigned long long pulls_done;        // halo pulls performed by this rank
-  unsigned push_ticket;                 // CTAs of the persistent kernel that finished their halo pushes
+  // push-model halo exchange (persistent kernels): element e of a vector sent to this rank
+  // lands in the two words 2e, 2e+1 at heap + ll_off -- (exchange number << 32) | low / high
+  // half of the value; self-validating, so the sender needs no fence and no flag
+  size_t ll_off;
 };
 
 struct State {

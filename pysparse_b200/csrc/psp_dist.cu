@@ -114,8 +114,11 @@ extern "C" int psp_dist_init(int rank, int world, size_t slot_elems, int nslots,
   DistHost &d = g_dist;
   if (d.ready) { set_error("psp_dist_init: already initialised"); return PSP_ERR_DIST; }
   d.rank = rank; d.world = world; d.slot_elems = slot_elems; d.nslots = nslots;
-  const size_t heap_bytes = sizeof(double) * slot_elems * (size_t)nslots;
+  // nslots work vectors, then the flag-in-data halo landing zone of the persistent kernels:
+  // two 8-byte words per vector element (see DistDev::ll_off)
+  const size_t heap_bytes = sizeof(double) * slot_elems * (size_t)(nslots + 2);
   PSP_CUDA(cudaMalloc((void **)&d.heap, heap_bytes ? heap_bytes : 8));
+  PSP_CUDA(cudaMemset(d.heap, 0, heap_bytes ? heap_bytes : 8));
   PSP_CUDA(cudaMalloc((void **)&d.ctl, sizeof(DistCtl)));
   PSP_CUDA(cudaMemset(d.ctl, 0, sizeof(DistCtl)));
   cudaIpcMemHandle_t h[2];
@@ -132,6 +135,7 @@ extern "C" int psp_dist_connect(const void *all_handles) {
   DistDev dd;
   memset(&dd, 0, sizeof dd);
   dd.rank = d.rank; dd.world = d.world;
+  dd.ll_off = d.slot_elems * (size_t)d.nslots;
   for (int w = 0; w < d.world; w++) {
     if (w == d.rank) { d.peer_heap[w] = d.heap; d.peer_ctl[w] = d.ctl; }
     else {
@@ -237,19 +241,24 @@ extern "C" int psp_dist_set_sendmap(psp_dmat *m, int nsend, const int *rows, con
     }
     mask |= 1u << dst_rank[s];
   }
-  cudaFree(dm->d_send_row); cudaFree(dm->d_send_rank); cudaFree(dm->d_send_off);
-  dm->d_send_row = dm->d_send_rank = dm->d_send_off = nullptr;
-  const size_t bytes = sizeof(int) * (size_t)(nsend > 0 ? nsend : 1);
-  if (cudaMalloc((void **)&dm->d_send_row, bytes) != cudaSuccess || cudaMalloc((void **)&dm->d_send_rank, bytes) != cudaSuccess ||
-      cudaMalloc((void **)&dm->d_send_off, bytes) != cudaSuccess) {
+  if (!d.ready) { set_error("psp_dist_set_sendmap: distributed layer not connected"); return PSP_ERR_DIST; }
+  cudaFree(dm->d_send_row); cudaFree(dm->d_send_dst);
+  dm->d_send_row = nullptr; dm->d_send_dst = nullptr;
+  const size_t cnt = (size_t)(nsend > 0 ? nsend : 1);
+  if (cudaMalloc((void **)&dm->d_send_row, sizeof(int) * cnt) != cudaSuccess ||
+      cudaMalloc((void **)&dm->d_send_dst, sizeof(unsigned long long *) * cnt) != cudaSuccess) {
     cudaGetLastError();
     set_error("psp_dist_set_sendmap: out of device memory");
     return PSP_ERR_NOMEM;
   }
   if (nsend) {
+    // element e of the neighbour's vector <-> words 2e, 2e+1 of its landing zone
+    std::vector<unsigned long long *> dst((size_t)nsend);
+    const size_t ll_off = d.slot_elems * (size_t)d.nslots;
+    for (int s = 0; s < nsend; s++)
+      dst[s] = reinterpret_cast<unsigned long long *>(d.peer_heap[dst_rank[s]] + ll_off) + 2 * (size_t)dst_off[s];
     PSP_CUDA(cudaMemcpy(dm->d_send_row, rows, sizeof(int) * (size_t)nsend, cudaMemcpyHostToDevice));
-    PSP_CUDA(cudaMemcpy(dm->d_send_rank, dst_rank, sizeof(int) * (size_t)nsend, cudaMemcpyHostToDevice));
-    PSP_CUDA(cudaMemcpy(dm->d_send_off, dst_off, sizeof(int) * (size_t)nsend, cudaMemcpyHostToDevice));
+    PSP_CUDA(cudaMemcpy(dm->d_send_dst, dst.data(), sizeof(unsigned long long *) * (size_t)nsend, cudaMemcpyHostToDevice));
   }
   dm->nsend = nsend;
   dm->sendmask = mask;
@@ -262,7 +271,7 @@ extern "C" void psp_dist_mat_destroy(psp_dmat *m) {
   if (!dm) return;
   if (dm->local) psp_mat_destroy(dm->local);
   cudaFree(dm->d_owner); cudaFree(dm->d_ridx);
-  cudaFree(dm->d_send_row); cudaFree(dm->d_send_rank); cudaFree(dm->d_send_off);
+  cudaFree(dm->d_send_row); cudaFree(dm->d_send_dst);
   delete dm;
 }
 

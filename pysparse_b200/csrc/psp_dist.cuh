@@ -23,7 +23,8 @@ struct DistMat {
   unsigned nbmask = 0;                    // ranks this rank pulls halo values from
   // push model (persistent kernels): local rows other ranks need, and where they go
   int nsend = 0;
-  int *d_send_row = nullptr, *d_send_rank = nullptr, *d_send_off = nullptr;
+  int *d_send_row = nullptr;
+  unsigned long long **d_send_dst = nullptr;   // landing-zone address of each entry in the neighbour's heap
   unsigned sendmask = 0;                  // ranks this rank pushes halo values to
   bool has_sendmap = false;
 };

@@ -61,13 +61,15 @@ struct PcgArgs {
   unsigned nbmask;
   // push model (send map present)
   int push, nsend;
-  const int *send_row, *send_rank, *send_off;
+  const int *send_row;
+  unsigned long long *const *send_dst;    // per entry: its two words in the neighbour's landing zone
   unsigned sendmask;
 };
 
 struct PersistSync {            // global scratch of the all-reduce / barrier (zeroed before each launch)
   unsigned ticket, pad;
   unsigned long long flag;      // generation of the last completed all-reduce
+  unsigned long long unpacked;  // halo exchanges x CTAs that have unpacked their share
   double result[2][kRedSlots + 1];
 };
 
@@ -78,7 +80,7 @@ struct PersistCtx {
   double *partials;
   PersistSync *sync;
   DistDev *dd;
-  unsigned long long seq, pubs, pulls, gen;
+  unsigned long long seq, pubs, pulls, gen, unpack_target;
   int parity;
   int debug;
 #ifdef PSP_PERSIST_PROF
@@ -292,39 +294,54 @@ __device__ __forceinline__ void publish_and_pull(cg::grid_group &grid, PersistCt
 
 // Push model (needs the send map, psp_dist_set_sendmap).  The search direction is double-
 // buffered (p_cur is read, p_new is written), so the boundary entries of p_new can be
-// computed and stored straight into the neighbours' heaps at the START of the p-update
-// phase (posted NVLink stores, nobody waits for them); by the time the phase ends they
-// have long been acknowledged, so the system-scope fence before the grid barrier is
-// cheap.  After the barrier one CTA raises the "arrived" counters in the neighbours'
-// control blocks.  The wait for the neighbours' entries (halo_wait, on LOCAL memory) is
-// deferred to the first row block that reads a halo column, so the whole exchange
-// overlaps the p update and the interior blocks.  No remote loads, no extra barrier.
-__device__ __forceinline__ void halo_fence(const PersistCtx &c, const PcgArgs &a) {
-  if (c.debug >= 1) return;
-  if ((long)blockIdx.x * blockDim.x < a.nsend) {       // this CTA issued remote stores
-    __syncthreads();
-    if (threadIdx.x == 0) __threadfence_system();
-  }
+// computed and sent at the START of the p-update phase: each one goes straight into the
+// neighbour's landing zone as two self-validating 8-byte words (half of the value + the
+// exchange number, DistDev::ll_off) -- posted NVLink stores, no fence, no flag, nobody
+// waits for them.  After the grid barrier that ends the phase every CTA unpacks its share
+// of the landing zone into the halo part of p_new (spinning on LOCAL memory until the
+// words of this exchange are there -- they left a whole phase ago) and draws a ticket;
+// the row blocks that read halo columns are scheduled last and wait for all tickets, so
+// the exchange overlaps the p update and the interior blocks.  No remote loads, no
+// system-scope fences (MEMBAR.SYS costs ~5 us here), no extra grid barrier.
+__device__ __forceinline__ void halo_send(const PersistCtx &c, const PcgArgs &a, long s, double v) {
+  const unsigned long long tag = (unsigned long long)(unsigned)(c.pubs + 1) << 32;
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+  unsigned long long *dst = a.send_dst[s];
+  st_relaxed_sys_u64(dst, tag | (bits & 0xffffffffull));
+  st_relaxed_sys_u64(dst + 1, tag | (bits >> 32));
 }
 
-// after the grid barrier that follows halo_fence()
-__device__ __forceinline__ void halo_signal(PersistCtx &c, const PcgArgs &a) {
+// after the grid barrier that completes the own part of `vec`
+__device__ __forceinline__ void halo_unpack(PersistCtx &c, const PcgArgs &a, double *vec) {
   DistDev *dd = c.dd;
   c.pubs += 1;
   c.pulls += 1;
+  c.unpack_target += gridDim.x;
   if (c.debug >= 1) return;
-  const int w = threadIdx.x;
-  if (blockIdx.x == 0 && w < dd->world && ((a.sendmask >> w) & 1u))
-    st_release_sys(&dd->ctl[w]->arrived[dd->rank], c.pubs);
+  const unsigned tag = (unsigned)c.pubs;
+  const unsigned long long *ll =
+      reinterpret_cast<const unsigned long long *>(dd->heap[dd->rank] + dd->ll_off) + 2 * (size_t)a.n;
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long h = (long)blockIdx.x * blockDim.x + threadIdx.x; h < a.nhalo; h += stride) {
+    unsigned long long w0, w1;                      // both words in one 16-byte load; each validates itself
+    do {
+      asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(ll + 2 * h) : "memory");
+    } while ((unsigned)(w0 >> 32) != tag || (unsigned)(w1 >> 32) != tag);
+    vec[a.n + h] = __longlong_as_double((long long)((w1 << 32) | (w0 & 0xffffffffull)));
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(&c.sync->unpacked, 1ull);
+  }
 }
 
+// before the first row block that reads a halo column
 __device__ __forceinline__ void halo_wait(PersistCtx &c, const PcgArgs &a) {
-  DistDev *dd = c.dd;
   if (c.debug >= 1) return;
   if (threadIdx.x == 0) {
-    for (int w = 0; w < dd->world; w++)
-      if ((a.nbmask >> w) & 1u)
-        while (ld_acquire_sys(&dd->ctl[dd->rank]->arrived[w]) < c.pulls) { }
+    while (ld_relaxed_gpu_u64(&c.sync->unpacked) < c.unpack_target) { }
+    __threadfence();
   }
   __syncthreads();
 }
@@ -344,7 +361,7 @@ __global__ void __launch_bounds__(kThreads, kPersistCtas) k_pcg_persist(PcgArgs 
   if (tid == 0) sS = *a.S;
   __syncthreads();
   PersistCtx c;
-  c.sS = &sS; c.tot = tot; c.red_sh = red_sh; c.partials = a.partials; c.sync = a.sync; c.parity = 0; c.gen = 0;
+  c.sS = &sS; c.tot = tot; c.red_sh = red_sh; c.partials = a.partials; c.sync = a.sync; c.parity = 0; c.gen = 0; c.unpack_target = 0;
   c.dd = sS.dist;
   c.debug = a.dist_debug;
   c.seq = c.pubs = c.pulls = 0;
@@ -371,12 +388,10 @@ __global__ void __launch_bounds__(kThreads, kPersistCtas) k_pcg_persist(PcgArgs 
   const double *xin = a.x;
   if (c.dd) {
     if (do_push)
-      for (long s = g0; s < a.nsend; s += gstride)
-        st_relaxed_sys_f64(c.dd->heap[a.send_rank[s]] + off_cur + a.send_off[s], a.x[a.send_row[s]]);
+      for (long s = g0; s < a.nsend; s += gstride) halo_send(c, a, s, a.x[a.send_row[s]]);
     for (long i = g0; i < n; i += gstride) p_cur[i] = a.x[i];
-    if (push) halo_fence(c, a);
     grid.sync();
-    if (push) halo_signal(c, a);
+    if (push) halo_unpack(c, a, p_cur);
     else publish_and_pull(grid, c, a, p_cur, off_cur);
     xin = p_cur;
   }
@@ -414,8 +429,7 @@ __global__ void __launch_bounds__(kThreads, kPersistCtas) k_pcg_persist(PcgArgs 
           const int row = a.send_row[s];
           const double ri = a.r[row];
           const double zi = a.dinv ? ri * a.dinv[row] : ri;
-          const double pv = first ? zi : zi + beta * p_cur[row];
-          st_relaxed_sys_f64(c.dd->heap[a.send_rank[s]] + off_new + a.send_off[s], pv);
+          halo_send(c, a, s, first ? zi : zi + beta * p_cur[row]);
         }
       }
       for (long i0 = g0; i0 < n; i0 += kVecUnroll * gstride) {
@@ -439,18 +453,17 @@ __global__ void __launch_bounds__(kThreads, kPersistCtas) k_pcg_persist(PcgArgs 
       }
     }
     PROF_T(c, 0);
-    if (push) halo_fence(c, a);
     grid.sync();
     PROF_T(c, 1);
     if (c.dd) {
-      if (push) halo_signal(c, a);
+      if (push) halo_unpack(c, a, p_new);
       else publish_and_pull(grid, c, a, p_new, off_new);
     }
     PROF_T(c, 2);
     {                                   // q = A p ; pq = p.q
       double acc[1] = {0.0};
       ring.template pass<false>(a.A, p_new, red_sh, [&](int r, double sum) { a.q[r] = sum; acc[0] += p_new[r] * sum; },
-                                [&] { if (push) halo_wait(c, a); });
+                                [&] { if (push) { PROF_T(c, 3); halo_wait(c, a); PROF_T(c, 13); } });
       ring.prefetch(a.A);
       PROF_T(c, 3);
       grid_allreduce<1, false>(c, acc, 0.0);
@@ -505,10 +518,10 @@ __global__ void __launch_bounds__(kThreads, kPersistCtas) k_pcg_persist(PcgArgs 
 #ifdef PSP_PERSIST_PROF
   if (blockIdx.x == 0 && tid == 0 && sS.it > 100) {
     const double k = 1.0 / (double)sS.it;
-    printf("persist prof (cycles/iter, it=%d): p-update %.0f | sync %.0f | halo push %.0f | pass %.0f | "
-           "allreduce[partials %.0f gridsync %.0f sum %.0f xgpu %.0f] | epi pq %.0f | update %.0f | epi upd %.0f\n",
-           sS.it, c.prof[0] * k, c.prof[1] * k, c.prof[2] * k, c.prof[3] * k, c.prof[8] * k, c.prof[9] * k, c.prof[10] * k,
-           c.prof[4] * k, c.prof[5] * k, c.prof[6] * k, c.prof[7] * k);
+    printf("persist prof (cycles/iter, it=%d): p-update %.0f | sync %.0f | halo unpack %.0f | pass %.0f | "
+           "allreduce[partials %.0f rest %.0f] | epi pq %.0f | update %.0f | epi upd %.0f | halo fence %.0f wait %.0f\n",
+           sS.it, c.prof[0] * k, c.prof[1] * k, c.prof[2] * k, c.prof[3] * k, c.prof[8] * k, (c.prof[9] + c.prof[4]) * k,
+           c.prof[5] * k, c.prof[6] * k, c.prof[7] * k, c.prof[11] * k, c.prof[13] * k);
   }
 #endif
 
@@ -549,8 +562,7 @@ int pcg_persist_launch(const psp_mat *M, int n, const double *b, double *x, doub
   a.nhalo = dm ? dm->nhalo : 0; a.nbmask = dm ? dm->nbmask : 0u;
   a.push = (dm && dm->has_sendmap && c.dist_push) ? 1 : 0;
   a.nsend = dm ? dm->nsend : 0; a.sendmask = dm ? dm->sendmask : 0u;
-  a.send_row = dm ? dm->d_send_row : nullptr; a.send_rank = dm ? dm->d_send_rank : nullptr;
-  a.send_off = dm ? dm->d_send_off : nullptr;
+  a.send_row = dm ? dm->d_send_row : nullptr; a.send_dst = dm ? dm->d_send_dst : nullptr;
   size_t p_slot_off = dm ? (size_t)(p - dist().heap) : 0;
   size_t p2_slot_off = dm ? (size_t)(p2 - dist().heap) : 0;
   // enough CTAs for the vector phases and the row blocks, never more than are co-resident

@@ -16,7 +16,8 @@ D.init(rank, world, nl + 2 * n * n + 64, nslots=4, group=ctl)
 A = D.ShardedMatrix(rowptr, slab["csr"][2], slab["csr"][1], slab["csr"][0], group=ctl)
 K = P.Precon.jacobi(None, np.full(nl, 6.0)); db = P.DeviceVector(nl, np.ones(nl)); dx = P.DeviceVector(nl)
 IT = 300
-for push, mode in ((1, 0), (0, 0), (1, 1), (0, 1), (1, 2), (0, 2), (1, 0), (0, 0)):
+MODES = [tuple(int(c) for c in m) for m in os.environ.get("DIAG_MODES", "10 00 11 01 12 02 10 00").split()]
+for push, mode in MODES:
     P.set_option("dist_push", push)
     P.set_option("dist_debug", mode)
     best = 1e9
