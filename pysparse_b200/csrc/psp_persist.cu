@@ -53,6 +53,7 @@ struct PcgArgs {
   State *S;
   double *partials;             // 2 x (kRedSlots + 1) x kMaxGrid, double-buffered
   PersistSync *sync;
+  DistDev *dd;                  // nullptr on a single GPU
   int l2_stream;
   int dist_debug;               // timing diagnostics (see Ctx::dist_debug)
   // multi-GPU
@@ -73,15 +74,17 @@ struct PersistSync {            // global scratch of the all-reduce / barrier (z
   double result[2][kRedSlots + 1];
 };
 
+// Per-thread view of the kernel's bookkeeping.  Kept small on purpose: the kernel runs
+// at 64 registers per thread (4 CTAs per SM), everything that can live in the parameter
+// bank (PcgArgs) or be recomputed does.
 struct PersistCtx {
   State *sS;                    // shared-memory copy of the solver state
   double *tot;                  // shared: kRedSlots + 1 totals
   double *red_sh;               // shared: 8 * (kRedSlots + 1) doubles
-  double *partials;
-  PersistSync *sync;
   DistDev *dd;
-  unsigned long long seq, pubs, pulls, gen, unpack_target;
-  int parity;
+  // low 32 bits of the reduction / halo-exchange sequence numbers (DistDev holds the
+  // 64-bit values between launches), all-reduce generation and unpack tickets expected
+  unsigned seq, pubs, gen, unpack_target;
   int debug;
 #ifdef PSP_PERSIST_PROF
   long long prof[16], t_last;
@@ -162,15 +165,14 @@ __device__ __forceinline__ void st_release_gpu_u64(unsigned long long *p, unsign
 // tot[kRedSlots] for the max) are valid in every thread of every CTA, and all global
 // writes made before the call are visible grid-wide.
 template <int NS, bool HASMAX>
-__device__ __forceinline__ void grid_allreduce(PersistCtx &c, const double *acc, double mx) {
+__device__ __forceinline__ void grid_allreduce(PersistCtx &c, const PcgArgs &a, const double *acc, double mx) {
   __shared__ int is_last;
   __shared__ unsigned box[kMaxRanks][8];
-  double *buf = c.partials + (size_t)c.parity * (kRedSlots + 1) * kMaxGrid;
-  double *res = c.sync->result[c.parity];
-  c.parity ^= 1;
-  const unsigned long long gen = ++c.gen;
+  const unsigned gen = ++c.gen;
+  double *buf = a.partials + (size_t)(gen & 1u) * (kRedSlots + 1) * kMaxGrid;
+  double *res = a.sync->result[gen & 1u];
   const bool xgpu = c.dd && c.debug < 2;
-  const unsigned long long seq = xgpu ? ++c.seq : c.seq;      // every CTA keeps count
+  const unsigned seq = xgpu ? ++c.seq : c.seq;                // every CTA keeps count
   double v[NS > 0 ? NS : 1];
 #pragma unroll
   for (int s = 0; s < NS; s++) v[s] = acc[s];
@@ -181,24 +183,24 @@ __device__ __forceinline__ void grid_allreduce(PersistCtx &c, const double *acc,
     for (int s = 0; s < NS; s++) buf[s * kMaxGrid + blockIdx.x] = v[s];
     if (HASMAX) buf[kRedSlots * kMaxGrid + blockIdx.x] = mx;
     __threadfence();
-    const unsigned t = atomicAdd(&c.sync->ticket, 1u);
+    const unsigned t = atomicAdd(&a.sync->ticket, 1u);
     __threadfence();
     is_last = (t == gridDim.x - 1);
   }
   __syncthreads();
   if (is_last) {
-    double a[NS > 0 ? NS : 1], m = 0.0;
+    double sm[NS > 0 ? NS : 1], m = 0.0;
 #pragma unroll
-    for (int s = 0; s < NS; s++) a[s] = 0.0;
+    for (int s = 0; s < NS; s++) sm[s] = 0.0;
     for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
 #pragma unroll
-      for (int s = 0; s < NS; s++) a[s] += __ldcg(buf + s * kMaxGrid + i);
+      for (int s = 0; s < NS; s++) sm[s] += __ldcg(buf + s * kMaxGrid + i);
       if (HASMAX) m = fmax(m, __ldcg(buf + kRedSlots * kMaxGrid + i));
     }
-    block_reduce_multi<NS, HASMAX>(a, m, c.red_sh);
+    block_reduce_multi<NS, HASMAX>(sm, m, c.red_sh);
     if (threadIdx.x == 0) {
 #pragma unroll
-      for (int s = 0; s < NS; s++) c.tot[s] = a[s];
+      for (int s = 0; s < NS; s++) c.tot[s] = sm[s];
       if (HASMAX) c.tot[kRedSlots] = m;
     }
     if (xgpu) {
@@ -212,7 +214,7 @@ __device__ __forceinline__ void grid_allreduce(PersistCtx &c, const double *acc,
       DistDev *dd = c.dd;
       const int W = dd->world, me = dd->rank;
       const int slot = (int)(seq % kMailRing);
-      const unsigned tag = (unsigned)seq;
+      const unsigned tag = seq;
       if ((int)threadIdx.x < W * 2 * NV) {
         const int w = threadIdx.x / (2 * NV), j = threadIdx.x % (2 * NV);
         const int k = j >> 1;
@@ -241,12 +243,12 @@ __device__ __forceinline__ void grid_allreduce(PersistCtx &c, const double *acc,
 #pragma unroll
       for (int s = 0; s < NS; s++) res[s] = c.tot[s];
       if (HASMAX) res[kRedSlots] = c.tot[kRedSlots];
-      c.sync->ticket = 0u;               // nobody draws again before the flag moves
+      a.sync->ticket = 0u;               // nobody draws again before the flag moves
       __threadfence();
-      st_release_gpu_u64(&c.sync->flag, gen);
+      st_release_gpu_u64(&a.sync->flag, (unsigned long long)gen);
     }
   } else if (threadIdx.x == 0) {
-    while (ld_relaxed_gpu_u64(&c.sync->flag) < gen) { }
+    while (ld_relaxed_gpu_u64(&a.sync->flag) < (unsigned long long)gen) { }
     __threadfence();
 #pragma unroll
     for (int s = 0; s < NS; s++) c.tot[s] = __ldcg(res + s);
@@ -273,12 +275,14 @@ __device__ __forceinline__ void publish_and_pull(cg::grid_group &grid, PersistCt
                                                  size_t slot_off) {
   DistDev *dd = c.dd;
   if (c.debug >= 1) { grid.sync(); return; }
+  // 64-bit publication number: the value at launch plus the exchanges done since (inside
+  // this kernel every publication is followed by exactly one pull)
+  const unsigned long long want = dd->pubs_done + (unsigned)(c.pubs - (unsigned)dd->pubs_done) + 1;
   c.pubs += 1;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     __threadfence_system();
-    st_release_sys(&dd->ctl[dd->rank]->pub, c.pubs);
+    st_release_sys(&dd->ctl[dd->rank]->pub, want);
   }
-  const unsigned long long want = c.pulls + 1;
   if (threadIdx.x == 0) {
     for (int w = 0; w < dd->world; w++)
       if ((a.nbmask >> w) & 1u)
@@ -288,7 +292,6 @@ __device__ __forceinline__ void publish_and_pull(cg::grid_group &grid, PersistCt
   const int stride = gridDim.x * blockDim.x;
   for (int h = blockIdx.x * blockDim.x + threadIdx.x; h < a.nhalo; h += stride)
     vec[a.n + h] = ld_relaxed_sys_f64(dd->heap[a.halo_owner[h]] + slot_off + a.halo_ridx[h]);
-  c.pulls += 1;
   grid.sync();
 }
 
@@ -303,8 +306,8 @@ __device__ __forceinline__ void publish_and_pull(cg::grid_group &grid, PersistCt
 // the row blocks that read halo columns are scheduled last and wait for all tickets, so
 // the exchange overlaps the p update and the interior blocks.  No remote loads, no
 // system-scope fences (MEMBAR.SYS costs ~5 us here), no extra grid barrier.
-__device__ __forceinline__ void halo_send(const PersistCtx &c, const PcgArgs &a, long s, double v) {
-  const unsigned long long tag = (unsigned long long)(unsigned)(c.pubs + 1) << 32;
+__device__ __forceinline__ void halo_send(const PersistCtx &c, const PcgArgs &a, unsigned s, double v) {
+  const unsigned long long tag = (unsigned long long)(c.pubs + 1u) << 32;
   const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
   unsigned long long *dst = a.send_dst[s];
   st_relaxed_sys_u64(dst, tag | (bits & 0xffffffffull));
@@ -315,10 +318,9 @@ __device__ __forceinline__ void halo_send(const PersistCtx &c, const PcgArgs &a,
 __device__ __forceinline__ void halo_unpack(PersistCtx &c, const PcgArgs &a, double *vec) {
   DistDev *dd = c.dd;
   c.pubs += 1;
-  c.pulls += 1;
   c.unpack_target += gridDim.x;
   if (c.debug >= 1) return;
-  const unsigned tag = (unsigned)c.pubs;
+  const unsigned tag = c.pubs;
   const unsigned long long *ll =
       reinterpret_cast<const unsigned long long *>(dd->heap[dd->rank] + dd->ll_off) + 2 * (size_t)a.n;
   const long stride = (long)gridDim.x * blockDim.x;
@@ -332,7 +334,7 @@ __device__ __forceinline__ void halo_unpack(PersistCtx &c, const PcgArgs &a, dou
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    atomicAdd(&c.sync->unpacked, 1ull);
+    atomicAdd(&a.sync->unpacked, 1ull);
   }
 }
 
@@ -340,13 +342,13 @@ __device__ __forceinline__ void halo_unpack(PersistCtx &c, const PcgArgs &a, dou
 __device__ __forceinline__ void halo_wait(PersistCtx &c, const PcgArgs &a) {
   if (c.debug >= 1) return;
   if (threadIdx.x == 0) {
-    while (ld_relaxed_gpu_u64(&c.sync->unpacked) < c.unpack_target) { }
+    while (ld_relaxed_gpu_u64(&a.sync->unpacked) < (unsigned long long)c.unpack_target) { }
     __threadfence();
   }
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(kThreads, kPersistCtas) k_pcg_persist(PcgArgs a, size_t p_slot_off, size_t p2_slot_off) {
+__global__ void __launch_bounds__(kThreads, kPersistCtas) k_pcg_persist(PcgArgs a, size_t p_slot_off) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t full[kPersistStages];
   __shared__ double red_sh[8 * (kRedSlots + 1)];
@@ -354,18 +356,19 @@ __global__ void __launch_bounds__(kThreads, kPersistCtas) k_pcg_persist(PcgArgs 
   __shared__ State sS;
   cg::grid_group grid = cg::this_grid();
   const int tid = threadIdx.x;
-  const long n = a.n;
-  const long gstride = (long)gridDim.x * blockDim.x;
-  const long g0 = (long)blockIdx.x * blockDim.x + tid;
+  // 32-bit indices: n < 2^31 and gridDim * blockDim < 2^20, so i + gstride cannot wrap
+  const unsigned n = (unsigned)a.n;
+  const unsigned gstride = gridDim.x * blockDim.x;
+  const unsigned g0 = blockIdx.x * blockDim.x + tid;
 
   if (tid == 0) sS = *a.S;
   __syncthreads();
   PersistCtx c;
-  c.sS = &sS; c.tot = tot; c.red_sh = red_sh; c.partials = a.partials; c.sync = a.sync; c.parity = 0; c.gen = 0; c.unpack_target = 0;
-  c.dd = sS.dist;
+  c.sS = &sS; c.tot = tot; c.red_sh = red_sh; c.gen = 0; c.unpack_target = 0;
+  c.dd = a.dd;
   c.debug = a.dist_debug;
-  c.seq = c.pubs = c.pulls = 0;
-  if (c.dd) { c.seq = c.dd->red_seq; c.pubs = c.dd->pubs_done; c.pulls = c.dd->pulls_done; }
+  c.seq = c.pubs = 0;
+  if (c.dd) { c.seq = (unsigned)c.dd->red_seq; c.pubs = (unsigned)c.dd->pubs_done; }
   const bool push = c.dd && a.push;
   const bool do_push = push && c.debug < 1;
 
@@ -376,23 +379,22 @@ __global__ void __launch_bounds__(kThreads, kPersistCtas) k_pcg_persist(PcgArgs 
   // ---- ||b||  (pcg.c:57-67)
   {
     double acc[1] = {0.0};
-    for (long i = g0; i < n; i += gstride) { double t = a.b[i]; acc[0] += t * t; }
-    grid_allreduce<1, false>(c, acc, 0.0);
+    for (unsigned i = g0; i < n; i += gstride) { double t = a.b[i]; acc[0] += t * t; }
+    grid_allreduce<1, false>(c, a, acc, 0.0);
     epilogue<1, false>(c, EPI_PCG_NORMB);
   }
   // the two buffers of the search direction (sharded: two slots of the symmetric heap)
   // (only the push model needs two: without it the update is done in place)
   double *p_cur = a.p, *p_new = push ? a.p2 : a.p;
-  size_t off_cur = p_slot_off, off_new = push ? p2_slot_off : p_slot_off;
   // ---- r = b - A x0  (pcg.c:72-89)
   const double *xin = a.x;
   if (c.dd) {
     if (do_push)
-      for (long s = g0; s < a.nsend; s += gstride) halo_send(c, a, s, a.x[a.send_row[s]]);
-    for (long i = g0; i < n; i += gstride) p_cur[i] = a.x[i];
+      for (unsigned s = g0; s < (unsigned)a.nsend; s += gstride) halo_send(c, a, s, a.x[a.send_row[s]]);
+    for (unsigned i = g0; i < n; i += gstride) p_cur[i] = a.x[i];
     grid.sync();
     if (push) halo_unpack(c, a, p_cur);
-    else publish_and_pull(grid, c, a, p_cur, off_cur);
+    else publish_and_pull(grid, c, a, a.p, p_slot_off);
     xin = p_cur;
   }
   ring.template pass<false>(a.A, xin, red_sh, [&](int r, double sum) { a.r[r] = sum; },
@@ -402,7 +404,7 @@ __global__ void __launch_bounds__(kThreads, kPersistCtas) k_pcg_persist(PcgArgs 
   {
     double acc[2] = {0.0, 0.0};
     const bool zero_rhs = (sS.phase == 1);
-    for (long i = g0; i < n; i += gstride) {
+    for (unsigned i = g0; i < n; i += gstride) {
       if (zero_rhs) { a.x[i] = 0.0; continue; }
       double t = a.b[i] - a.r[i];
       a.r[i] = t;
@@ -410,7 +412,7 @@ __global__ void __launch_bounds__(kThreads, kPersistCtas) k_pcg_persist(PcgArgs 
       double z = a.dinv ? t * a.dinv[i] : t;
       acc[1] += t * z;
     }
-    grid_allreduce<2, false>(c, acc, 0.0);
+    grid_allreduce<2, false>(c, a, acc, 0.0);
     epilogue<2, false>(c, EPI_PCG_RESID0_J);
   }
 
@@ -425,18 +427,18 @@ __global__ void __launch_bounds__(kThreads, kPersistCtas) k_pcg_persist(PcgArgs 
       const bool first = (sS.it == 1);
       if (do_push) {
         // boundary entries first, straight to the neighbours (same arithmetic as below)
-        for (long s = g0; s < a.nsend; s += gstride) {
+        for (unsigned s = g0; s < (unsigned)a.nsend; s += gstride) {
           const int row = a.send_row[s];
           const double ri = a.r[row];
           const double zi = a.dinv ? ri * a.dinv[row] : ri;
           halo_send(c, a, s, first ? zi : zi + beta * p_cur[row]);
         }
       }
-      for (long i0 = g0; i0 < n; i0 += kVecUnroll * gstride) {
+      for (unsigned i0 = g0; i0 < n; i0 += kVecUnroll * gstride) {
         double ri[kVecUnroll], di[kVecUnroll], pi[kVecUnroll];
 #pragma unroll
         for (int u = 0; u < kVecUnroll; u++) {
-          const long i = i0 + u * gstride;
+          const unsigned i = i0 + u * gstride;
           const bool ok = i < n;
           ri[u] = ok ? a.r[i] : 0.0;
           di[u] = (ok && a.dinv) ? a.dinv[i] : 1.0;
@@ -444,7 +446,7 @@ __global__ void __launch_bounds__(kThreads, kPersistCtas) k_pcg_persist(PcgArgs 
         }
 #pragma unroll
         for (int u = 0; u < kVecUnroll; u++) {
-          const long i = i0 + u * gstride;
+          const unsigned i = i0 + u * gstride;
           if (i < n) {
             const double zi = a.dinv ? ri[u] * di[u] : ri[u];
             p_new[i] = first ? zi : zi + beta * pi[u];
@@ -457,7 +459,7 @@ __global__ void __launch_bounds__(kThreads, kPersistCtas) k_pcg_persist(PcgArgs 
     PROF_T(c, 1);
     if (c.dd) {
       if (push) halo_unpack(c, a, p_new);
-      else publish_and_pull(grid, c, a, p_new, off_new);
+      else publish_and_pull(grid, c, a, a.p, p_slot_off);    // pull model: p is updated in place
     }
     PROF_T(c, 2);
     {                                   // q = A p ; pq = p.q
@@ -466,7 +468,7 @@ __global__ void __launch_bounds__(kThreads, kPersistCtas) k_pcg_persist(PcgArgs 
                                 [&] { if (push) { PROF_T(c, 3); halo_wait(c, a); PROF_T(c, 13); } });
       ring.prefetch(a.A);
       PROF_T(c, 3);
-      grid_allreduce<1, false>(c, acc, 0.0);
+      grid_allreduce<1, false>(c, a, acc, 0.0);
       PROF_T(c, 4);
       epilogue<1, false>(c, EPI_PCG_PQ);
       PROF_T(c, 5);
@@ -476,11 +478,11 @@ __global__ void __launch_bounds__(kThreads, kPersistCtas) k_pcg_persist(PcgArgs 
       const double alpha = sS.v[V_ALPHA];
       const bool scan = (sS.stag == 0);
       double acc[2] = {0.0, 0.0}, mx = 0.0;
-      for (long i0 = g0; i0 < n; i0 += kVecUnroll * gstride) {
+      for (unsigned i0 = g0; i0 < n; i0 += kVecUnroll * gstride) {
         double xv[kVecUnroll], pv[kVecUnroll], rv[kVecUnroll], qv[kVecUnroll], dv[kVecUnroll];
 #pragma unroll
         for (int u = 0; u < kVecUnroll; u++) {
-          const long i = i0 + u * gstride;
+          const unsigned i = i0 + u * gstride;
           const bool ok = i < n;
           xv[u] = ok ? a.x[i] : 0.0;
           pv[u] = ok ? p_new[i] : 0.0;
@@ -490,7 +492,7 @@ __global__ void __launch_bounds__(kThreads, kPersistCtas) k_pcg_persist(PcgArgs 
         }
 #pragma unroll
         for (int u = 0; u < kVecUnroll; u++) {
-          const long i = i0 + u * gstride;
+          const unsigned i = i0 + u * gstride;
           if (i < n) {
             const double xi = xv[u], pi = pv[u];
             if (scan) {
@@ -507,13 +509,12 @@ __global__ void __launch_bounds__(kThreads, kPersistCtas) k_pcg_persist(PcgArgs 
         }
       }
       PROF_T(c, 6);
-      grid_allreduce<2, true>(c, acc, mx);
+      grid_allreduce<2, true>(c, a, acc, mx);
       PROF_T(c, 4);
       epilogue<2, true>(c, EPI_PCG_UPDATE_J);
       PROF_T(c, 7);
     }
     { double *t = p_cur; p_cur = p_new; p_new = t; }
-    { const size_t t = off_cur; off_cur = off_new; off_new = t; }
   }
 #ifdef PSP_PERSIST_PROF
   if (blockIdx.x == 0 && tid == 0 && sS.it > 100) {
@@ -528,7 +529,10 @@ __global__ void __launch_bounds__(kThreads, kPersistCtas) k_pcg_persist(PcgArgs 
   ring.drain(a.A);
   if (blockIdx.x == 0 && tid == 0) {
     *a.S = sS;
-    if (c.dd) { c.dd->red_seq = c.seq; c.dd->pubs_done = c.pubs; c.dd->pulls_done = c.pulls; }
+    if (c.dd) {                       // 64-bit sequence numbers: add what this launch did (wrap-safe)
+      const unsigned nred = c.seq - (unsigned)c.dd->red_seq, nexch = c.pubs - (unsigned)c.dd->pubs_done;
+      c.dd->red_seq += nred; c.dd->pubs_done += nexch; c.dd->pulls_done += nexch;
+    }
   }
 }
 
@@ -557,19 +561,18 @@ int pcg_persist_launch(const psp_mat *M, int n, const double *b, double *x, doub
   a.A.blk = reinterpret_cast<const int4 *>(M->d_blk);
   a.A.nint = M->nint;
   a.n = n; a.b = b; a.x = x; a.r = r; a.p = p; a.p2 = p2; a.q = q; a.dinv = dinv;
-  a.S = c.state; a.partials = g_partials2; a.sync = g_sync; a.l2_stream = l2_stream_for(n); a.dist_debug = (int)c.dist_debug;
+  a.S = c.state; a.partials = g_partials2; a.sync = g_sync; a.dd = dm ? dist().dev : nullptr; a.l2_stream = l2_stream_for(n); a.dist_debug = (int)c.dist_debug;
   a.halo_owner = dm ? dm->d_owner : nullptr; a.halo_ridx = dm ? dm->d_ridx : nullptr;
   a.nhalo = dm ? dm->nhalo : 0; a.nbmask = dm ? dm->nbmask : 0u;
   a.push = (dm && dm->has_sendmap && c.dist_push) ? 1 : 0;
   a.nsend = dm ? dm->nsend : 0; a.sendmask = dm ? dm->sendmask : 0u;
   a.send_row = dm ? dm->d_send_row : nullptr; a.send_dst = dm ? dm->d_send_dst : nullptr;
   size_t p_slot_off = dm ? (size_t)(p - dist().heap) : 0;
-  size_t p2_slot_off = dm ? (size_t)(p2 - dist().heap) : 0;
   // enough CTAs for the vector phases and the row blocks, never more than are co-resident
   long long want = (n + kThreads - 1) / kThreads;
   if (M->nb > want) want = M->nb;
   int grid = (int)(want < resident ? (want > 0 ? want : 1) : resident);
-  void *args[] = {&a, &p_slot_off, &p2_slot_off};
+  void *args[] = {&a, &p_slot_off};
   PSP_CUDA(cudaLaunchCooperativeKernel((const void *)k_pcg_persist, dim3(grid), dim3(kThreads), args, smem_bytes, c.stream));
   c.launches++;
   return PSP_OK;

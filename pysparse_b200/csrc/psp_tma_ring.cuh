@@ -70,14 +70,13 @@ template <int STAGES>
 struct Ring {
   unsigned char *smem;                    // STAGES * kStageBytes, 128-byte aligned
   uint64_t *full;                         // STAGES mbarriers
-  uint64_t policy;                        // L2 evict-first policy (0: no hint)
+  bool l2_stream;                         // bulk copies carry the L2 evict-first hint
   uint32_t phases;                        // parity bit per stage
   int cursor;                             // next stage to consume
   int prefetched;                         // number of blocks of the next pass already in flight
 
-  __device__ __forceinline__ void init(unsigned char *smem_, uint64_t *full_, bool l2_stream) {
-    smem = smem_; full = full_; phases = 0; cursor = 0; prefetched = 0; policy = 0;
-    if (l2_stream) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+  __device__ __forceinline__ void init(unsigned char *smem_, uint64_t *full_, bool l2_stream_) {
+    smem = smem_; full = full_; phases = 0; cursor = 0; prefetched = 0; l2_stream = l2_stream_;
     if (threadIdx.x == 0) {
 #pragma unroll
       for (int s = 0; s < STAGES; s++) mbar_init(&full[s], 1);
@@ -95,8 +94,10 @@ struct Ring {
     const uint32_t nr = (uint32_t)((d.z + 1 - rbase + 3) & ~3);
     unsigned char *st = smem + (size_t)stage * kStageBytes;
     mbar_expect_tx(&full[stage], ne * 12u + nr * 4u);
-    if (policy) {
+    if (l2_stream) {
       // the matrix is read once per product: evict-first keeps the (re-used) vectors in L2
+      uint64_t policy;                                // made on the spot: not worth two registers in every thread
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
       tma_load_1d_hint(st, A.val + base, ne * 8u, &full[stage], policy);
       tma_load_1d_hint(st + kStageVal, A.col + base, ne * 4u, &full[stage], policy);
       tma_load_1d_hint(st + kStageVal + kStageCol, A.ind + rbase, nr * 4u, &full[stage], policy);
