@@ -244,18 +244,46 @@ def run_single(args):
         "iters_per_step": iters / args.steps,
         "pcg_iter_algorithmic_GBps": alg_bytes_pcg_iter(N, nnz) * iters / (ms * 1e-3) / 1e9,
     }
-    if n_spmv:
-        per = spmv_ms / n_spmv * 1e-3
-        ach = alg_bytes_spmv(N, nnz) / per / 1e9
-        traffic = None
+    def traffic_of(key):
         tp = os.path.join(ROOT, "profiles", "spmv_traffic.json")
         if os.path.exists(tp) and args.grid == 256:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-        line["roofline"] = {"bound": "hbm", "kernel": "k_spmv_tma<2,true> (CSR SpMV + fused p.q dot)",
-                            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                            "traffic": traffic, "peak_source": peak_src, "launches_sampled": n_spmv,
-                            "avg_launch_us": per * 1e6, "algorithmic_bytes_per_launch": alg_bytes_spmv(N, nnz),
-                            "gflops": 2 * nnz / per / 1e9}
+            return json.load(open(tp)).get(key)
+        return None
+
+    def spmv_roofline(n_spmv, spmv_ms):
+        per = spmv_ms / n_spmv * 1e-3
+        ach = alg_bytes_spmv(N, nnz) / per / 1e9
+        return {"bound": "hbm", "kernel": "k_spmv_tma<2,true> (CSR SpMV + fused p.q dot)",
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": traffic_of("dram_bytes_per_launch"), "peak_source": peak_src, "launches_sampled": n_spmv,
+                "avg_launch_us": per * 1e6, "algorithmic_bytes_per_launch": alg_bytes_spmv(N, nnz),
+                "gflops": 2 * nnz / per / 1e9}
+
+    if n_spmv:
+        line["roofline"] = spmv_roofline(n_spmv, spmv_ms)
+    else:
+        # The solve ran as ONE persistent cooperative kernel (k_pcg_persist): that launch is
+        # the dominant kernel.  Algorithmic bytes per launch = iterations x the per-iteration
+        # figure of DESIGN.md (matrix once + 13 vector streams); duration = the CUDA-event
+        # time of the timed region / launches (it contains nothing else but a memset).
+        per = ms * 1e-3 / args.steps
+        nb = alg_bytes_pcg_iter(N, nnz) * iters / args.steps
+        line["roofline"] = {"bound": "hbm", "kernel": "k_pcg_persist (whole PCG + Jacobi solve in one cooperative launch)",
+                            "achieved": nb / per / 1e9, "peak": peak, "unit": "GB/s", "frac": nb / per / 1e9 / peak,
+                            "traffic": traffic_of("pcg_persist_dram_bytes_per_launch"), "peak_source": peak_src,
+                            "launches_sampled": args.steps, "avg_launch_us": per * 1e6,
+                            "algorithmic_bytes_per_launch": nb,
+                            "algorithmic_bytes_per_iteration": alg_bytes_pcg_iter(N, nnz)}
+        # for continuity: the stand-alone SpMV + dot kernel, sampled in a short solve on the
+        # per-phase path (not part of the timed region)
+        P.set_option("pcg_persist", 0)
+        P.spmv_timing(4)
+        dx.fill(0.0)
+        P.solve("pcg", A, db, dx, args.tol, 64, K, dev=True)
+        n2, ms2 = P.spmv_timing(0)
+        P.set_option("pcg_persist", -1)
+        if n2:
+            line["roofline_spmv"] = spmv_roofline(n2, ms2)
     if args.sweep:
         line["spmv_sweep"] = spmv_sweep(P)
     if not args.no_cpu:

@@ -329,5 +329,9 @@ def set_option(name: str, value: int) -> None:
     check(lib.psp_set_option(name.encode(), value))
 
 
+def get_option(name: str) -> int:
+    return int(lib.psp_get_option(name.encode()))
+
+
 def synchronize() -> None:
     check(lib.psp_synchronize())
