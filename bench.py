@@ -277,9 +277,11 @@ def run_single(args):
         # for continuity: the stand-alone SpMV + dot kernel, sampled in a short solve on the
         # per-phase path (not part of the timed region)
         P.set_option("pcg_persist", 0)
-        P.spmv_timing(4)
         dx.fill(0.0)
-        P.solve("pcg", A, db, dx, args.tol, 64, K, dev=True)
+        P.solve("pcg", A, db, dx, args.tol, 32, K, dev=True)      # settle on the per-phase path first
+        P.spmv_timing(8)
+        dx.fill(0.0)
+        P.solve("pcg", A, db, dx, args.tol, 256, K, dev=True)
         n2, ms2 = P.spmv_timing(0)
         P.set_option("pcg_persist", -1)
         if n2:
