@@ -14,6 +14,7 @@
 #define PY_ARRAY_UNIQUE_SYMBOL psp_spmatrix_ARRAY_API
 #include "psp_host.h"
 #include <math.h>
+#include <stdarg.h>
 
 static PyTypeObject LLMatType, CSRMatType, SSSMatType;
 static PyObject *SpMatrix_ErrorObject;
@@ -739,6 +740,10 @@ static PyObject *LLMat_norm(LLMatObject *self, PyObject *args)
   }
   int by_col = !strcmp(p, "1");
   if (!by_col && strcmp(p, "inf")) { PyErr_SetString(PyExc_ValueError, "unknown norm"); return NULL; }
+  if (self->issym) {                              /* as the reference (test/test_spmatrix.py:193-199) */
+    PyErr_SetString(PyExc_NotImplementedError, "Not implemented for symmetric matrices");
+    return NULL;
+  }
   int len = by_col ? n : m;
   if (self->issym) len = m;
   double *s = (double *)calloc((size_t)(len > 0 ? len : 1), sizeof(double));
@@ -813,73 +818,510 @@ static PyObject *LLMat_get_shape(LLMatObject *self, void *c) { return Py_BuildVa
 static PyObject *LLMat_get_nnz(LLMatObject *self, void *c) { return PyLong_FromLong(self->nnz); }
 static PyObject *LLMat_get_issym(LLMatObject *self, void *c) { return PyLong_FromLong(self->issym); }
 
-/* ---- subscripting: integer pairs and slices ------------------------------- */
-static int norm_index(PyObject *o, int dim, Py_ssize_t *start, Py_ssize_t *stop, Py_ssize_t *step, Py_ssize_t *len, int *is_int)
+/* ---- subscripting: integers, slices, lists / tuples / integer arrays ----------
+ * (getSubMatrix_FromList / setSubMatrix_FromList, ll_mat.c:632-1250; documented in
+ * doc/pysparse/source/spmatrix.rst:94-260).  All paths walk the stored entries of the
+ * selected rows -- never the dense l0 x l1 index space -- except for the assignment of
+ * a non-zero scalar, which by definition fills a dense block.
+ *
+ * Deliberate differences from the reference snapshot (its fancy-indexing rewrite left its
+ * own test/test_spmatrix.py:84-123 failing):
+ *   - a stepped column slice selects (col - start) % step == 0 (the reference tests
+ *     col % step, which is only right when start is a multiple of step);
+ *   - A[rows, cols] = M REPLACES the block (entries of A in the block that are zero in M
+ *     are removed), which is what the reference's tests and documentation expect; the
+ *     snapshot only overlays the stored entries of M;
+ *   - a symmetric M stands for the full symmetric matrix wherever it is assigned, and
+ *     slicing a symmetric matrix returns the full (general) sub-matrix.
+ */
+typedef struct {
+  int kind;                      /* 0 single integer, 1 slice, 2 explicit index list */
+  Py_ssize_t start, step, len;   /* kinds 0 / 1 */
+  long *list;                    /* kind 2: len indices, wrapped and bounds-checked (owned) */
+} IndexSet;
+
+static void index_set_free(IndexSet *s) { free(s->list); s->list = NULL; }
+
+static int index_set_parse(PyObject *o, int dim, IndexSet *s)
 {
-  if (PyLong_Check(o)) {
-    long v = PyLong_AsLong(o);
-    if (v == -1 && PyErr_Occurred()) return -1;
-    while (v < 0) v += dim;                      /* ll_mat.c:644-645 */
-    if (v >= dim) { PyErr_SetString(PyExc_IndexError, "Index out of bounds"); return -1; }
-    *start = v; *stop = v + 1; *step = 1; *len = 1; *is_int = 1;
-    return 0;
-  }
+  s->kind = 0; s->start = 0; s->step = 1; s->len = 0; s->list = NULL;
   if (PySlice_Check(o)) {
-    if (PySlice_Unpack(o, start, stop, step) < 0) return -1;
-    *len = PySlice_AdjustIndices(dim, start, stop, *step);
-    *is_int = 0;
+    Py_ssize_t stop;
+    if (PySlice_Unpack(o, &s->start, &stop, &s->step) < 0) return -1;
+    s->len = PySlice_AdjustIndices(dim, &s->start, &stop, s->step);
+    s->kind = 1;
     return 0;
   }
-  PyErr_SetString(PyExc_IndexError, "Index must be an integer or a slice");
+  if (PyIndex_Check(o) && !PyArray_Check(o)) {
+    Py_ssize_t v = PyNumber_AsSsize_t(o, PyExc_IndexError);
+    if (v == -1 && PyErr_Occurred()) return -1;
+    while (v < 0 && dim > 0) v += dim;            /* ll_mat.c:644-645 */
+    if (v < 0 || v >= dim) { PyErr_SetString(PyExc_IndexError, "Index out of bounds"); return -1; }
+    s->start = v; s->len = 1;
+    return 0;
+  }
+  if (PyList_Check(o) || PyTuple_Check(o) || PyArray_Check(o)) {
+    PyArrayObject *raw = (PyArrayObject *)PyArray_FROM_O(o), *a = NULL;
+    if (raw && (PyArray_ISINTEGER(raw) || PyArray_SIZE(raw) == 0))     /* no silent truncation of floats */
+      a = (PyArrayObject *)PyArray_FROM_OTF((PyObject *)raw, NPY_LONG, NPY_ARRAY_IN_ARRAY | NPY_ARRAY_FORCECAST);
+    Py_XDECREF(raw);
+    if (!a) { PyErr_Clear(); PyErr_SetString(PyExc_IndexError, "Invalid list item"); return -1; }
+    if (PyArray_NDIM(a) != 1) { Py_DECREF(a); PyErr_SetString(PyExc_IndexError, "index arrays must be 1-dimensional"); return -1; }
+    s->len = (Py_ssize_t)PyArray_SIZE(a);
+    s->list = (long *)malloc(sizeof(long) * (size_t)(s->len > 0 ? s->len : 1));
+    if (!s->list) { Py_DECREF(a); PyErr_NoMemory(); return -1; }
+    const long *p = (const long *)PyArray_DATA(a);
+    for (Py_ssize_t k = 0; k < s->len; k++) {
+      long v = p[k];
+      if (v < 0) v += dim;
+      if (v < 0 || v >= dim) { Py_DECREF(a); index_set_free(s); PyErr_SetString(PyExc_IndexError, "Index out of bounds"); return -1; }
+      s->list[k] = v;
+    }
+    Py_DECREF(a);
+    s->kind = 2;
+    return 0;
+  }
+  PyErr_SetString(PyExc_IndexError, "Index must be an integer, a slice, a list or an integer array");
   return -1;
+}
+
+static inline long index_at(const IndexSet *s, Py_ssize_t k) { return s->kind == 2 ? s->list[k] : (long)(s->start + k * s->step); }
+
+/* column -> positions in an index set: arithmetic for slices, chains for lists (a column
+ * may occur several times in a list) */
+typedef struct { const IndexSet *s; int *head, *next; } ColMap;
+
+static void colmap_free(ColMap *m) { free(m->head); free(m->next); m->head = m->next = NULL; }
+
+static int colmap_build(ColMap *m, const IndexSet *s, int dim)
+{
+  m->s = s; m->head = m->next = NULL;
+  if (s->kind != 2) return 0;
+  m->head = (int *)malloc(sizeof(int) * (size_t)(dim > 0 ? dim : 1));
+  m->next = (int *)malloc(sizeof(int) * (size_t)(s->len > 0 ? s->len : 1));
+  if (!m->head || !m->next) { colmap_free(m); PyErr_NoMemory(); return -1; }
+  for (int c = 0; c < dim; c++) m->head[c] = -1;
+  for (Py_ssize_t k = s->len - 1; k >= 0; k--) { m->next[k] = m->head[s->list[k]]; m->head[s->list[k]] = (int)k; }
+  return 0;
+}
+
+/* first position of column c in the set, or -1 */
+static inline int colmap_first(const ColMap *m, int c)
+{
+  const IndexSet *s = m->s;
+  if (s->kind == 2) return m->head[c];
+  if (s->len == 0) return -1;
+  Py_ssize_t d = c - s->start;
+  if (s->step < 0) { d = -d; }
+  const Py_ssize_t st = s->step < 0 ? -s->step : s->step;
+  if (d < 0 || d % st != 0 || d / st >= s->len) return -1;
+  return (int)(d / st);
+}
+static inline int colmap_next(const ColMap *m, int pos) { return m->s->kind == 2 ? m->next[pos] : -1; }
+
+static PyObject *LLMat_copy(LLMatObject *self, PyObject *noargs);
+static PyObject *LLMat_generalize(LLMatObject *self, PyObject *noargs);
+
+static PyObject *ll_get_submatrix(LLMatObject *self, const IndexSet *r, const IndexSet *c)
+{
+  LLMatObject *src = self, *tmp = NULL, *dst = NULL;
+  ColMap cm = {0};
+  if (self->issym) {                              /* the full matrix, not just the stored triangle */
+    tmp = (LLMatObject *)LLMat_copy(self, NULL);
+    if (!tmp) return NULL;
+    PyObject *none = LLMat_generalize(tmp, NULL);
+    if (!none) { Py_DECREF(tmp); return NULL; }
+    Py_DECREF(none);
+    src = tmp;
+  }
+  int dim[2] = {(int)r->len, (int)c->len};
+  dst = (LLMatObject *)SpMatrix_NewLLMatObject(dim, 0, 16, self->storeZeros);
+  if (!dst || colmap_build(&cm, c, src->dim[1])) goto fail;
+  for (Py_ssize_t a = 0; a < r->len; a++) {
+    const LLRow *row = &src->rows[index_at(r, a)];
+    for (int k = 0; k < row->len; k++)
+      for (int j = colmap_first(&cm, row->col[k]); j >= 0; j = colmap_next(&cm, j))
+        if (SpMatrix_LLMatSetItem(dst, (int)a, j, row->val[k])) goto fail;
+  }
+  colmap_free(&cm);
+  Py_XDECREF(tmp);
+  return (PyObject *)dst;
+fail:
+  colmap_free(&cm);
+  Py_XDECREF(tmp);
+  Py_XDECREF(dst);
+  return NULL;
+}
+
+/* remove the stored entries of the block rows x cols */
+static int ll_clear_block(LLMatObject *self, const IndexSet *r, const IndexSet *c)
+{
+  ColMap cm;
+  if (colmap_build(&cm, c, self->dim[1])) return -1;
+  for (Py_ssize_t a = 0; a < r->len; a++) {
+    LLRow *row = &self->rows[index_at(r, a)];
+    int w = 0;
+    for (int k = 0; k < row->len; k++) {
+      if (colmap_first(&cm, row->col[k]) >= 0) continue;
+      row->col[w] = row->col[k]; row->val[w] = row->val[k]; w++;
+    }
+    self->nnz -= row->len - w;
+    row->len = w;
+  }
+  colmap_free(&cm);
+  self->version++;
+  return 0;
+}
+
+static int upper_write_error(void)
+{
+  PyErr_SetString(PyExc_IndexError, "Writing to upper triangle of symmetric matrix");
+  return -1;
+}
+
+static int ll_set_scalar(LLMatObject *self, const IndexSet *r, const IndexSet *c, double v)
+{
+  if (r->len == 0 || c->len == 0) return 0;
+  if (self->issym) {                              /* nothing is written if any target is above the diagonal */
+    long minrow = index_at(r, 0), maxcol = index_at(c, 0);
+    for (Py_ssize_t a = 1; a < r->len; a++) if (index_at(r, a) < minrow) minrow = index_at(r, a);
+    for (Py_ssize_t b = 1; b < c->len; b++) if (index_at(c, b) > maxcol) maxcol = index_at(c, b);
+    if (minrow < maxcol) return upper_write_error();
+  }
+  if (v == 0.0 && !self->storeZeros) return ll_clear_block(self, r, c);
+  for (Py_ssize_t a = 0; a < r->len; a++)
+    for (Py_ssize_t b = 0; b < c->len; b++)
+      if (SpMatrix_LLMatSetItem(self, (int)index_at(r, a), (int)index_at(c, b), v)) return -1;
+  return 0;
+}
+
+static int ll_set_matrix(LLMatObject *self, const IndexSet *r, const IndexSet *c, LLMatObject *mat)
+{
+  if (mat->dim[0] != r->len || mat->dim[1] != c->len) { PyErr_SetString(PyExc_ValueError, "Matrix shapes are different"); return -1; }
+  LLMatObject *own = NULL;
+  int rc = -1;
+  if (mat == self) {                              /* A[p, q] = A: read from a snapshot */
+    own = (LLMatObject *)LLMat_copy(self, NULL);
+    if (!own) return -1;
+    mat = own;
+  }
+  if (self->issym && !mat->issym) {               /* a general block may not reach above the diagonal */
+    for (int a = 0; a < mat->dim[0]; a++)
+      for (int k = 0; k < mat->rows[a].len; k++)
+        if (index_at(r, a) < index_at(c, mat->rows[a].col[k])) { upper_write_error(); goto done; }
+  }
+  if (ll_clear_block(self, r, c)) goto done;
+  for (int a = 0; a < mat->dim[0]; a++) {
+    const LLRow *row = &mat->rows[a];
+    for (int k = 0; k < row->len; k++) {
+      const int b = row->col[k];
+      const double v = row->val[k];
+      long i = index_at(r, a), j = index_at(c, b);
+      if (!(self->issym && i < j) && SpMatrix_LLMatSetItem(self, (int)i, (int)j, v)) goto done;
+      if (mat->issym && a != b) {                 /* the mirrored entry (b, a) of a symmetric source */
+        i = index_at(r, b); j = index_at(c, a);
+        if (!(self->issym && i < j) && SpMatrix_LLMatSetItem(self, (int)i, (int)j, v)) goto done;
+      }
+    }
+  }
+  rc = 0;
+done:
+  Py_XDECREF(own);
+  return rc;
+}
+
+static int parse_index_pair(LLMatObject *self, PyObject *idx, IndexSet *r, IndexSet *c)
+{
+  if (!PyTuple_Check(idx) || PyTuple_GET_SIZE(idx) != 2) { PyErr_SetString(PyExc_IndexError, "There must be exactly two indices"); return -1; }
+  if (index_set_parse(PyTuple_GET_ITEM(idx, 0), self->dim[0], r)) return -1;
+  if (index_set_parse(PyTuple_GET_ITEM(idx, 1), self->dim[1], c)) { index_set_free(r); return -1; }
+  return 0;
 }
 
 static PyObject *LLMat_subscript(LLMatObject *self, PyObject *idx)
 {
-  if (!PyTuple_Check(idx) || PyTuple_GET_SIZE(idx) != 2) { PyErr_SetString(PyExc_IndexError, "Index must be a pair"); return NULL; }
-  Py_ssize_t s0, e0, st0, l0, s1, e1, st1, l1; int int0, int1;
-  if (norm_index(PyTuple_GET_ITEM(idx, 0), self->dim[0], &s0, &e0, &st0, &l0, &int0)) return NULL;
-  if (norm_index(PyTuple_GET_ITEM(idx, 1), self->dim[1], &s1, &e1, &st1, &l1, &int1)) return NULL;
-  if (int0 && int1) return PyFloat_FromDouble(SpMatrix_LLMatGetItem(self, (int)s0, (int)s1));
-  int dim[2] = {(int)l0, (int)l1};
-  LLMatObject *dst = (LLMatObject *)SpMatrix_NewLLMatObject(dim, 0, 16, self->storeZeros);
-  if (!dst) return NULL;
-  for (Py_ssize_t a = 0; a < l0; a++)
-    for (Py_ssize_t b = 0; b < l1; b++) {
-      double v = SpMatrix_LLMatGetItem(self, (int)(s0 + a * st0), (int)(s1 + b * st1));
-      if (v != 0.0 && SpMatrix_LLMatSetItem(dst, (int)a, (int)b, v)) { Py_DECREF(dst); return NULL; }
-    }
-  return (PyObject *)dst;
+  IndexSet r, c;
+  if (parse_index_pair(self, idx, &r, &c)) return NULL;
+  PyObject *ret;
+  if (r.kind == 0 && c.kind == 0) ret = PyFloat_FromDouble(SpMatrix_LLMatGetItem(self, (int)r.start, (int)c.start));
+  else ret = ll_get_submatrix(self, &r, &c);
+  index_set_free(&r); index_set_free(&c);
+  return ret;
 }
 
 static int LLMat_ass_subscript(LLMatObject *self, PyObject *idx, PyObject *value)
 {
   if (!value) { PyErr_SetString(PyExc_TypeError, "cannot delete matrix entries"); return -1; }
-  if (!PyTuple_Check(idx) || PyTuple_GET_SIZE(idx) != 2) { PyErr_SetString(PyExc_IndexError, "Index must be a pair"); return -1; }
-  Py_ssize_t s0, e0, st0, l0, s1, e1, st1, l1; int int0, int1;
-  if (norm_index(PyTuple_GET_ITEM(idx, 0), self->dim[0], &s0, &e0, &st0, &l0, &int0)) return -1;
-  if (norm_index(PyTuple_GET_ITEM(idx, 1), self->dim[1], &s1, &e1, &st1, &l1, &int1)) return -1;
+  IndexSet r, c;
+  if (parse_index_pair(self, idx, &r, &c)) return -1;
+  int rc;
   if (PyObject_TypeCheck(value, &LLMatType)) {
-    LLMatObject *src = (LLMatObject *)value;
-    if (src->dim[0] != l0 || src->dim[1] != l1) { PyErr_SetString(PyExc_ValueError, "Matrix shapes are different"); return -1; }
-    /* clear the target block, then copy (symmetric targets only receive i >= j) */
-    for (Py_ssize_t a = 0; a < l0; a++)
-      for (Py_ssize_t b = 0; b < l1; b++) {
-        int i = (int)(s0 + a * st0), j = (int)(s1 + b * st1);
-        if (self->issym && i < j) continue;
-        double v = SpMatrix_LLMatGetItem(src, (int)a, (int)b);
-        if (SpMatrix_LLMatSetItem(self, i, j, v)) return -1;
-      }
-    return 0;
+    if (r.kind == 0 && c.kind == 0) { PyErr_SetString(PyExc_ValueError, "Value must be double"); rc = -1; }
+    else rc = ll_set_matrix(self, &r, &c, (LLMatObject *)value);
+  } else {
+    double v = PyFloat_AsDouble(value);
+    if (v == -1.0 && PyErr_Occurred()) { PyErr_Clear(); PyErr_SetString(PyExc_ValueError, "Value must be double"); rc = -1; }
+    else if (r.kind == 0 && c.kind == 0) rc = SpMatrix_LLMatSetItem(self, (int)r.start, (int)c.start, v);
+    else rc = ll_set_scalar(self, &r, &c, v);
   }
-  double v = PyFloat_AsDouble(value);
-  if (v == -1.0 && PyErr_Occurred()) { PyErr_Clear(); PyErr_SetString(PyExc_ValueError, "Value must be double"); return -1; }
-  for (Py_ssize_t a = 0; a < l0; a++)
-    for (Py_ssize_t b = 0; b < l1; b++)
-      if (SpMatrix_LLMatSetItem(self, (int)(s0 + a * st0), (int)(s1 + b * st1), v)) return -1;
+  index_set_free(&r); index_set_free(&c);
+  return rc;
+}
+
+/* ---- masks, element-matrix assembly, scaling, row / column deletion ----------- */
+static PyArrayObject *as_long_vector(PyObject *o, Py_ssize_t len, const char *what)
+{
+  PyArrayObject *a = (PyArrayObject *)PyArray_FROM_OTF(o, NPY_LONG, NPY_ARRAY_IN_ARRAY);
+  if (!a || PyArray_NDIM(a) != 1 || (len >= 0 && PyArray_SIZE(a) != len)) {
+    Py_XDECREF(a);
+    PyErr_Clear();
+    PyErr_Format(PyExc_ValueError, "%s must be a 1D integer NumPy array of appropriate length", what);
+    return NULL;
+  }
+  return a;
+}
+
+/* A.update_add_mask(B, ind0, ind1, mask0, mask1): A[ind0[i], ind1[j]] += B[i, j] where
+ * mask0[i] and mask1[j]   (LLMat_update_add_mask, ll_mat.c:2201-2291; spmatrix.rst:358-382).
+ * B is read as documented, B[i, j]; the reference snapshot addresses its C-contiguous copy
+ * of B column-major, i.e. reads B[j, i] of a square B -- the same for the symmetric element
+ * matrices the method is meant for. */
+static PyObject *LLMat_update_add_mask(LLMatObject *self, PyObject *args)
+{
+  PyObject *bIn, *i0In, *i1In, *m0In, *m1In, *ret = NULL;
+  if (self->issym) { PyErr_SetString(SpMatrix_ErrorObject, "Method not allowed for symmetric matrices"); return NULL; }
+  if (!PyArg_ParseTuple(args, "OOOOO", &bIn, &i0In, &i1In, &m0In, &m1In)) return NULL;
+  PyArrayObject *b = (PyArrayObject *)PyArray_FROM_OTF(bIn, NPY_DOUBLE, NPY_ARRAY_IN_ARRAY);
+  PyArrayObject *i0 = NULL, *i1 = NULL, *m0 = NULL, *m1 = NULL;
+  if (!b) return NULL;
+  if (PyArray_NDIM(b) != 2) { PyErr_SetString(PyExc_ValueError, "arg 1 must be a 2-dimensional double array"); goto done; }
+  if (!(i0 = as_long_vector(i0In, -1, "arg 2")) || !(i1 = as_long_vector(i1In, -1, "arg 3"))) goto done;
+  const Py_ssize_t l0 = PyArray_SIZE(i0), l1 = PyArray_SIZE(i1);
+  m0 = (PyArrayObject *)PyArray_FROM_OTF(m0In, NPY_LONG, NPY_ARRAY_IN_ARRAY);
+  m1 = (PyArrayObject *)PyArray_FROM_OTF(m1In, NPY_LONG, NPY_ARRAY_IN_ARRAY);
+  if (!m0 || !m1) goto done;
+  if (PyArray_NDIM(m0) != 1 || PyArray_NDIM(m1) != 1 || PyArray_SIZE(m0) != l0 || PyArray_SIZE(m1) != l1) {
+    PyErr_SetString(PyExc_ValueError, "Shapes of index and mask array do not match");
+    goto done;
+  }
+  if (PyArray_DIM(b, 0) != l0 || PyArray_DIM(b, 1) != l1) {
+    PyErr_SetString(PyExc_ValueError, "Shapes of input matrix and index arrays do not match");
+    goto done;
+  }
+  const double *bv = (const double *)PyArray_DATA(b);
+  const long *p0 = (const long *)PyArray_DATA(i0), *p1 = (const long *)PyArray_DATA(i1);
+  const long *q0 = (const long *)PyArray_DATA(m0), *q1 = (const long *)PyArray_DATA(m1);
+  for (Py_ssize_t i = 0; i < l0; i++) {
+    if (!q0[i]) continue;
+    long r = p0[i];
+    if (r < 0) r += self->dim[0];
+    if (r < 0 || r >= self->dim[0]) { PyErr_SetString(PyExc_IndexError, "element of arg 2 out of range"); goto done; }
+    for (Py_ssize_t j = 0; j < l1; j++) {
+      if (!q1[j]) continue;
+      long c = p1[j];
+      if (c < 0) c += self->dim[1];
+      if (c < 0 || c >= self->dim[1]) { PyErr_SetString(PyExc_IndexError, "element of arg 3 out of range"); goto done; }
+      if (SpMatrix_LLMatUpdateItemAdd(self, (int)r, (int)c, bv[i * l1 + j])) goto done;
+    }
+  }
+  Py_INCREF(Py_None);
+  ret = Py_None;
+done:
+  Py_XDECREF(b); Py_XDECREF(i0); Py_XDECREF(i1); Py_XDECREF(m0); Py_XDECREF(m1);
+  return ret;
+}
+
+/* A.update_add_mask_sym(B, ind, mask): the lower triangle of the (symmetric) element matrix
+ * B is added where mask[i] and mask[j]: once, below the diagonal, for a symmetric A; to both
+ * (ind[i], ind[j]) and (ind[j], ind[i]) for a general one   (ll_mat.c:2306-2391). */
+static PyObject *LLMat_update_add_mask_sym(LLMatObject *self, PyObject *args)
+{
+  PyObject *bIn, *iIn, *mIn, *ret = NULL;
+  if (!PyArg_ParseTuple(args, "OOO", &bIn, &iIn, &mIn)) return NULL;
+  PyArrayObject *b = (PyArrayObject *)PyArray_FROM_OTF(bIn, NPY_DOUBLE, NPY_ARRAY_IN_ARRAY);
+  PyArrayObject *ind = NULL, *mask = NULL;
+  if (!b) return NULL;
+  if (PyArray_NDIM(b) != 2) { PyErr_SetString(PyExc_ValueError, "arg 1 must be a 2-dimensional double array"); goto done; }
+  if (!(ind = as_long_vector(iIn, -1, "arg 2"))) goto done;
+  const Py_ssize_t len = PyArray_SIZE(ind);
+  mask = (PyArrayObject *)PyArray_FROM_OTF(mIn, NPY_LONG, NPY_ARRAY_IN_ARRAY);
+  if (!mask) goto done;
+  if (PyArray_NDIM(mask) != 1 || PyArray_SIZE(mask) != len) { PyErr_SetString(PyExc_ValueError, "Shapes of index and mask array do not match"); goto done; }
+  if (PyArray_DIM(b, 0) != len || PyArray_DIM(b, 1) != len) { PyErr_SetString(PyExc_ValueError, "Shapes of input matrix and index arrays do not match"); goto done; }
+  const double *bv = (const double *)PyArray_DATA(b);
+  const long *p = (const long *)PyArray_DATA(ind), *q = (const long *)PyArray_DATA(mask);
+  for (Py_ssize_t i = 0; i < len; i++) {
+    if (!q[i]) continue;
+    long r = p[i];
+    if (r < 0) r += self->dim[0];
+    if (r < 0 || r >= self->dim[0]) { PyErr_SetString(PyExc_IndexError, "element of arg 2 out of range"); goto done; }
+    for (Py_ssize_t j = 0; j <= i; j++) {
+      if (!q[j]) continue;
+      long c = p[j];
+      if (c < 0) c += self->dim[1];
+      if (c < 0 || c >= self->dim[1]) { PyErr_SetString(PyExc_IndexError, "element of arg 2 out of range"); goto done; }
+      const double v = bv[i * len + j];
+      if (self->issym) {
+        if (SpMatrix_LLMatUpdateItemAdd(self, (int)(r > c ? r : c), (int)(r > c ? c : r), v)) goto done;
+      } else {
+        if (SpMatrix_LLMatUpdateItemAdd(self, (int)r, (int)c, v)) goto done;
+        if (r != c && SpMatrix_LLMatUpdateItemAdd(self, (int)c, (int)r, v)) goto done;
+      }
+    }
+  }
+  Py_INCREF(Py_None);
+  ret = Py_None;
+done:
+  Py_XDECREF(b); Py_XDECREF(ind); Py_XDECREF(mask);
+  return ret;
+}
+
+/* A.col_scale(v): A[i, j] *= v[j];  A.row_scale(v): A[i, j] *= v[i] -- on the stored entries
+ * (LLMat_col_scale / LLMat_row_scale, ll_mat.c:1473-1571) */
+static PyObject *scale_by_vector(LLMatObject *self, PyObject *args, int by_col)
+{
+  PyObject *vIn;
+  if (!PyArg_ParseTuple(args, "O", &vIn)) return NULL;
+  PyArrayObject *v = (PyArrayObject *)PyArray_FROM_OTF(vIn, NPY_DOUBLE, NPY_ARRAY_IN_ARRAY);
+  if (!v) { PyErr_Clear(); PyErr_SetString(SpMatrix_ErrorObject, "Cannot read input vector."); return NULL; }
+  if (PyArray_NDIM(v) != 1 || PyArray_SIZE(v) != self->dim[by_col ? 1 : 0]) {
+    Py_DECREF(v);
+    PyErr_SetString(SpMatrix_ErrorObject, "Size of scaling vector does not match the matrix.");
+    return NULL;
+  }
+  const double *s = (const double *)PyArray_DATA(v);
+  for (int i = 0; i < self->dim[0]; i++) {
+    LLRow *row = &self->rows[i];
+    for (int k = 0; k < row->len; k++) row->val[k] *= by_col ? s[row->col[k]] : s[i];
+  }
+  self->version++;
+  Py_DECREF(v);
+  Py_RETURN_NONE;
+}
+static PyObject *LLMat_col_scale(LLMatObject *self, PyObject *args) { return scale_by_vector(self, args, 1); }
+static PyObject *LLMat_row_scale(LLMatObject *self, PyObject *args) { return scale_by_vector(self, args, 0); }
+
+/* A.delete_rows(mask) / delete_cols(mask) / delete_rowcols(mask): row / column i is REMOVED
+ * where mask[i] == 0, the matrix shrinks   (ll_mat.c:2764-2995, spmatrix.rst:468-481) */
+static void ll_drop_rows(LLMatObject *self, const long *mask)
+{
+  int newm = 0;
+  for (int i = 0; i < self->dim[0]; i++) {
+    if (mask[i]) { self->rows[newm++] = self->rows[i]; continue; }
+    self->nnz -= self->rows[i].len;
+    free(self->rows[i].col); free(self->rows[i].val);
+  }
+  for (int i = newm; i < self->dim[0]; i++) memset(&self->rows[i], 0, sizeof(LLRow));
+  self->dim[0] = newm;
+}
+
+static int ll_drop_cols(LLMatObject *self, const long *mask)
+{
+  const int n = self->dim[1];
+  int *newcol = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+  if (!newcol) { PyErr_NoMemory(); return -1; }
+  int newn = 0;
+  for (int j = 0; j < n; j++) newcol[j] = mask[j] ? newn++ : -1;
+  for (int i = 0; i < self->dim[0]; i++) {
+    LLRow *row = &self->rows[i];
+    int w = 0;
+    for (int k = 0; k < row->len; k++) {
+      const int c = newcol[row->col[k]];
+      if (c < 0) continue;
+      row->col[w] = c; row->val[w] = row->val[k]; w++;
+    }
+    self->nnz -= row->len - w;
+    row->len = w;
+  }
+  free(newcol);
+  self->dim[1] = newn;
   return 0;
 }
-static PyMappingMethods LLMat_as_mapping = {0, (binaryfunc)LLMat_subscript, (objobjargproc)LLMat_ass_subscript};
+
+static PyObject *delete_by_mask(LLMatObject *self, PyObject *args, int rows, int cols)
+{
+  PyObject *mIn;
+  if (!PyArg_ParseTuple(args, "O", &mIn)) return NULL;
+  if (self->issym && !(rows && cols)) { PyErr_SetString(SpMatrix_ErrorObject, "method not allowed for symmetric matrices"); return NULL; }
+  if (rows && cols && self->dim[0] != self->dim[1]) { PyErr_SetString(PyExc_ValueError, "delete_rowcols needs a square matrix"); return NULL; }
+  PyArrayObject *mask = as_long_vector(mIn, self->dim[rows ? 0 : 1], "mask");
+  if (!mask) return NULL;
+  const long *m = (const long *)PyArray_DATA(mask);
+  int rc = 0;
+  /* columns first: a symmetric matrix keeps (i, j), i >= j, exactly when both survive, and
+   * the surviving pairs stay below the diagonal because the renumbering is monotone */
+  if (cols) rc = ll_drop_cols(self, m);
+  if (!rc && rows) ll_drop_rows(self, m);
+  self->version++;
+  Py_DECREF(mask);
+  if (rc) return NULL;
+  Py_RETURN_NONE;
+}
+static PyObject *LLMat_delete_rows(LLMatObject *self, PyObject *args) { return delete_by_mask(self, args, 1, 0); }
+static PyObject *LLMat_delete_cols(LLMatObject *self, PyObject *args) { return delete_by_mask(self, args, 0, 1); }
+static PyObject *LLMat_delete_rowcols(LLMatObject *self, PyObject *args) { return delete_by_mask(self, args, 1, 1); }
+
+/* len(A) = number of matrix positions (LLMat_length, ll_mat.c:3195) */
+static Py_ssize_t LLMat_length(LLMatObject *self) { return (Py_ssize_t)self->dim[0] * self->dim[1]; }
+static PyMappingMethods LLMat_as_mapping = {(lenfunc)LLMat_length, (binaryfunc)LLMat_subscript, (objobjargproc)LLMat_ass_subscript};
+
+/* str(A) / print(A): the text LLMatType_print (ll_mat.c:3085-3157) writes -- a dense picture
+ * for matrices of at most 500 x 20, the list of stored entries otherwise */
+typedef struct { char *p; size_t len, cap; } StrBuf;
+static int sb_printf(StrBuf *b, const char *fmt, ...)
+{
+  va_list ap;
+  for (;;) {
+    va_start(ap, fmt);
+    int n = vsnprintf(b->p + b->len, b->cap - b->len, fmt, ap);
+    va_end(ap);
+    if (n < 0) return -1;
+    if ((size_t)n < b->cap - b->len) { b->len += (size_t)n; return 0; }
+    size_t ncap = (b->cap + (size_t)n + 64) * 2;
+    char *np_ = (char *)realloc(b->p, ncap);
+    if (!np_) return -1;
+    b->p = np_; b->cap = ncap;
+  }
+}
+
+static PyObject *LLMat_str(LLMatObject *a)
+{
+  StrBuf b = {(char *)malloc(256), 0, 256};
+  if (!b.p) return PyErr_NoMemory();
+  const char *sym = a->issym ? "symmetric" : "general";
+  int rc = 0;
+  if (a->dim[1] <= 20 && a->dim[0] <= 500) {
+    rc |= sb_printf(&b, "ll_mat(%s, [%d,%d]):\n", sym, a->dim[0], a->dim[1]);
+    for (int i = 0; i < a->dim[0] && !rc; i++) {
+      const LLRow *r = &a->rows[i];
+      int k = 0;
+      for (int j = 0; j < a->dim[1] && !rc; j++) {
+        double val = 0.0;
+        if (k < r->len && r->col[k] == j) val = r->val[k++];
+        if (val != 0.0) {
+          int ex = (int)log10(fabs(val));
+          if (abs(ex) <= 4) rc |= sb_printf(&b, "%9.*f ", ex < 0 ? 6 : 6 - ex, val);
+          else rc |= sb_printf(&b, "%9.1e ", val);
+        } else if (!a->issym || i > j) rc |= sb_printf(&b, " -------- ");
+      }
+      rc |= sb_printf(&b, "\n");
+    }
+  } else if (a->nnz == 0) {
+    rc |= sb_printf(&b, "ll_mat(%s, [%d,%d])", sym, a->dim[0], a->dim[1]);
+  } else {
+    int first = 1;
+    rc |= sb_printf(&b, "ll_mat(%s, [%d,%d], [", sym, a->dim[0], a->dim[1]);
+    for (int i = 0; i < a->dim[0] && !rc; i++)
+      for (int k = 0; k < a->rows[i].len && !rc; k++) {
+        rc |= sb_printf(&b, "%s(%d,%d): %g", first ? "" : ", ", i, a->rows[i].col[k], a->rows[i].val[k]);
+        first = 0;
+      }
+    rc |= sb_printf(&b, "])");
+  }
+  PyObject *o = rc ? PyErr_NoMemory() : PyUnicode_FromStringAndSize(b.p, (Py_ssize_t)b.len);
+  free(b.p);
+  return o;
+}
 
 static PyMethodDef LLMat_methods[] = {
   {"matvec", (PyCFunction)LLMat_matvec, METH_VARARGS, "A.matvec(x, y)\n\ncompute the sparse matrix-vector product y := A * x."},
@@ -900,12 +1342,21 @@ static PyMethodDef LLMat_methods[] = {
   {"take", (PyCFunction)LLMat_take, METH_VARARGS, "a.take(b, id1, id2): b[i] = a[id1[i], id2[i]]"},
   {"find", (PyCFunction)LLMat_find, METH_NOARGS, "(val, irow, jcol) = a.find()"},
   {"update_add_at", (PyCFunction)LLMat_update_add_at, METH_VARARGS, "a.update_add_at(b, id1, id2): a[id1[i], id2[i]] += b[i]"},
+  {"update_add_mask", (PyCFunction)LLMat_update_add_mask, METH_VARARGS, "A.update_add_mask(B, ind0, ind1, mask0, mask1): A[ind0[i], ind1[j]] += B[i, j] where mask0[i] and mask1[j]"},
+  {"update_add_mask_sym", (PyCFunction)LLMat_update_add_mask_sym, METH_VARARGS, "A.update_add_mask_sym(B, ind, mask): symmetric element-matrix assembly"},
+  {"col_scale", (PyCFunction)LLMat_col_scale, METH_VARARGS, "A.col_scale(v): scale the i-th column of A by v[i] in place"},
+  {"row_scale", (PyCFunction)LLMat_row_scale, METH_VARARGS, "A.row_scale(v): scale the i-th row of A by v[i] in place"},
+  {"delete_rows", (PyCFunction)LLMat_delete_rows, METH_VARARGS, "A.delete_rows(mask): remove (in place) the rows with mask[i] == 0"},
+  {"delete_cols", (PyCFunction)LLMat_delete_cols, METH_VARARGS, "A.delete_cols(mask): remove (in place) the columns with mask[i] == 0"},
+  {"delete_rowcols", (PyCFunction)LLMat_delete_rowcols, METH_VARARGS, "A.delete_rowcols(mask): remove (in place) rows and columns with mask[i] == 0"},
   {NULL, NULL}
 };
+static PyObject *LLMat_get_storeZeros(LLMatObject *self, void *c) { return PyLong_FromLong(self->storeZeros); }
 static PyGetSetDef LLMat_getset[] = {
   {"shape", (getter)LLMat_get_shape, NULL, NULL, NULL},
   {"nnz", (getter)LLMat_get_nnz, NULL, NULL, NULL},
   {"issym", (getter)LLMat_get_issym, NULL, NULL, NULL},
+  {"storeZeros", (getter)LLMat_get_storeZeros, NULL, NULL, NULL},
   {"_psp_mat", (getter)LLMat_get_dev, NULL, "device handle (PyCapsule)", NULL},
   {NULL}
 };
@@ -1154,6 +1605,7 @@ PyMODINIT_FUNC PyInit_spmatrix(void)
   import_array();
   static PyTypeObject zero = {PyVarObject_HEAD_INIT(NULL, 0)};
   LLMatType = zero; CSRMatType = zero; SSSMatType = zero;
+  LLMatType.tp_str = (reprfunc)LLMat_str;
   if (init_type(&LLMatType, "pysparse_b200.sparse.spmatrix.ll_mat", sizeof(LLMatObject), (destructor)LLMat_dealloc, LLMat_methods, LLMat_getset, &LLMat_as_mapping) < 0 ||
       init_type(&CSRMatType, "pysparse_b200.sparse.spmatrix.csr_mat", sizeof(CSRMatObject), (destructor)CSRMat_dealloc, CSRMat_methods, CSRMat_getset, &CSRMat_as_mapping) < 0 ||
       init_type(&SSSMatType, "pysparse_b200.sparse.spmatrix.sss_mat", sizeof(SSSMatObject), (destructor)SSSMat_dealloc, SSSMat_methods, SSSMat_getset, &SSSMat_as_mapping) < 0)
@@ -1163,7 +1615,11 @@ PyMODINIT_FUNC PyInit_spmatrix(void)
   Py_INCREF(&LLMatType); PyModule_AddObject(m, "LLMatType", (PyObject *)&LLMatType);
   Py_INCREF(&CSRMatType); PyModule_AddObject(m, "CSRMatType", (PyObject *)&CSRMatType);
   Py_INCREF(&SSSMatType); PyModule_AddObject(m, "SSSMatType", (PyObject *)&SSSMatType);
-  SpMatrix_ErrorObject = PyUnicode_FromString("spmatrix.error");
+  /* the reference's "spmatrix.error" is a Python-2 string exception (spmatrixmodule.c:373);
+   * here it is an exception class of that name */
+  SpMatrix_ErrorObject = PyErr_NewException("spmatrix.error", NULL, NULL);
+  if (!SpMatrix_ErrorObject) return NULL;
+  Py_INCREF(SpMatrix_ErrorObject);
   PyModule_AddObject(m, "error", SpMatrix_ErrorObject);
 
   SpMatrix_API[PSP_API_LLMatType] = (void *)&LLMatType;
