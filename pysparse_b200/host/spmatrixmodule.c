@@ -1562,21 +1562,120 @@ static PyObject *sss_from_arrays(PyObject *self, PyObject *args)
   return (PyObject *)op;
 }
 
-static PyObject *not_on_hot_path(PyObject *self, PyObject *args)
+/* ---- sparse x sparse products of the assembly container ----------------------
+ * matrixmultiply(A, B) = A B, dot(A, B) = A^T B, symdot(A[, d]) = A^T diag(d) A
+ * (LLMat_matrixmultiply / LLMat_dot / LLMat_symdot, ll_mat.c:3462-3796).  Like shift() and
+ * scale() these are operations OF THE HOST CONTAINER (the reference's are too); their
+ * result is an ll_mat, whose matvec is the GPU path.  Every entry of the result adds its
+ * terms in the reference's order, so the values are bit-identical to the reference's. */
+static PyObject *LLMat_matrixmultiply(PyObject *module, PyObject *args)
 {
-  PyErr_SetString(PyExc_NotImplementedError,
-                  "sparse x sparse products (matrixmultiply / dot / symdot) are outside the SpMV / Krylov hot path "
-                  "pysparse_b200 accelerates (SURVEY.md section 8(f))");
+  LLMatObject *A, *B, *C = NULL, *Afull = NULL;
+  double *acc = NULL;
+  int *mark = NULL, *cols = NULL;
+  if (!PyArg_ParseTuple(args, "O!O!", &LLMatType, &A, &LLMatType, &B)) return NULL;
+  if (A->dim[1] != B->dim[0]) { PyErr_SetString(PyExc_ValueError, "matrix dimensions must agree"); return NULL; }
+  if (B->issym) {
+    PyErr_SetString(PyExc_NotImplementedError, A->issym ? "multiply of two symmetric matrices not supported"
+                                                        : "multiply of an unsymmetric and a symmetric matrix not supported");
+    return NULL;
+  }
+  int dim[2] = {A->dim[0], B->dim[1]};
+  C = (LLMatObject *)SpMatrix_NewLLMatObject(dim, 0, 1000, A->storeZeros == 1 && B->storeZeros == 1);
+  if (!C) return NULL;
+  if (A->issym) {              /* row i of the full matrix, ascending columns: the order in which the
+                                  reference's sym-unsym loop adds the terms of row i of the product */
+    Afull = (LLMatObject *)LLMat_copy(A, NULL);
+    PyObject *none = Afull ? LLMat_generalize(Afull, NULL) : NULL;
+    if (!none) goto fail;
+    Py_DECREF(none);
+    A = Afull;
+  }
+  const int n = B->dim[1];
+  acc = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+  mark = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+  cols = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+  if (!acc || !mark || !cols) { PyErr_NoMemory(); goto fail; }
+  for (int j = 0; j < n; j++) mark[j] = -1;
+  for (int i = 0; i < A->dim[0]; i++) {
+    const LLRow *ra = &A->rows[i];
+    int cnt = 0;
+    for (int k = 0; k < ra->len; k++) {
+      const double va = ra->val[k];
+      const LLRow *rb = &B->rows[ra->col[k]];
+      for (int l = 0; l < rb->len; l++) {
+        const int j = rb->col[l];
+        if (mark[j] != i) { mark[j] = i; cols[cnt++] = j; acc[j] = va * rb->val[l]; }
+        else acc[j] += va * rb->val[l];
+      }
+    }
+    for (int t = 0; t < cnt; t++)
+      if (SpMatrix_LLMatSetItem(C, i, cols[t], acc[cols[t]])) goto fail;
+  }
+  free(acc); free(mark); free(cols);
+  Py_XDECREF(Afull);
+  return (PyObject *)C;
+fail:
+  free(acc); free(mark); free(cols);
+  Py_XDECREF(Afull);
+  Py_XDECREF(C);
   return NULL;
+}
+
+static PyObject *LLMat_dot(PyObject *module, PyObject *args)
+{
+  LLMatObject *A, *B;
+  if (!PyArg_ParseTuple(args, "O!O!", &LLMatType, &A, &LLMatType, &B)) return NULL;
+  if (A->dim[0] != B->dim[0]) { PyErr_SetString(PyExc_ValueError, "matrix dimensions must agree"); return NULL; }
+  if (A->issym || B->issym) { PyErr_SetString(PyExc_NotImplementedError, "ddot operation with symmetric matrices not supported"); return NULL; }
+  int dim[2] = {A->dim[1], B->dim[1]};
+  LLMatObject *C = (LLMatObject *)SpMatrix_NewLLMatObject(dim, 0, 1000, A->storeZeros == 1 && B->storeZeros == 1);
+  if (!C) return NULL;
+  for (int i = 0; i < A->dim[0]; i++) {
+    const LLRow *ra = &A->rows[i], *rb = &B->rows[i];
+    for (int k = 0; k < ra->len; k++)
+      for (int l = 0; l < rb->len; l++)
+        if (SpMatrix_LLMatUpdateItemAdd(C, ra->col[k], rb->col[l], ra->val[k] * rb->val[l])) { Py_DECREF(C); return NULL; }
+  }
+  return (PyObject *)C;
+}
+
+static PyObject *LLMat_symdot(PyObject *module, PyObject *args)
+{
+  LLMatObject *A;
+  PyObject *dIn = NULL;
+  PyArrayObject *d = NULL;
+  if (!PyArg_ParseTuple(args, "O!|O", &LLMatType, &A, &dIn)) return NULL;
+  if (dIn && dIn != Py_None) {
+    d = (PyArrayObject *)PyArray_FROM_OTF(dIn, NPY_DOUBLE, NPY_ARRAY_IN_ARRAY);
+    if (!d || PyArray_NDIM(d) != 1) { Py_XDECREF(d); PyErr_Clear(); PyErr_SetString(SpMatrix_ErrorObject, "Could not read scaling vector."); return NULL; }
+    if (PyArray_SIZE(d) != A->dim[0]) { Py_DECREF(d); PyErr_SetString(SpMatrix_ErrorObject, "Scaling vector has wrong dimension."); return NULL; }
+  }
+  if (A->issym) { Py_XDECREF(d); PyErr_SetString(PyExc_NotImplementedError, "symdot operation with symmetric matrices not supported"); return NULL; }
+  int dim[2] = {A->dim[1], A->dim[1]};
+  LLMatObject *C = (LLMatObject *)SpMatrix_NewLLMatObject(dim, 1, 1000, A->storeZeros == 1);
+  if (!C) { Py_XDECREF(d); return NULL; }
+  const double *dv = d ? (const double *)PyArray_DATA(d) : NULL;
+  for (int i = 0; i < A->dim[0]; i++) {
+    const LLRow *r = &A->rows[i];
+    for (int k = 0; k < r->len; k++) {
+      double va = r->val[k];
+      if (dv) va *= dv[i];
+      for (int l = 0; l < r->len && r->col[l] <= r->col[k]; l++)
+        if (SpMatrix_LLMatUpdateItemAdd(C, r->col[k], r->col[l], va * r->val[l])) { Py_XDECREF(d); Py_DECREF(C); return NULL; }
+    }
+  }
+  Py_XDECREF(d);
+  return (PyObject *)C;
 }
 
 static PyMethodDef spmatrix_methods[] = {
   {"ll_mat", LLMat_zeros, METH_VARARGS, "ll_mat(n, m, sizeHint=1000, storeZeros=0)"},
   {"ll_mat_sym", LLMat_sym_zeros, METH_VARARGS, "ll_mat_sym(n, sizeHint=1000, storeZeros=0)"},
   {"ll_mat_from_mtx", LLMat_from_mtx, METH_VARARGS, "ll_mat_from_mtx(fileName)"},
-  {"matrixmultiply", not_on_hot_path, METH_VARARGS, NULL},
-  {"dot", not_on_hot_path, METH_VARARGS, NULL},
-  {"symdot", not_on_hot_path, METH_VARARGS, NULL},
+  {"matrixmultiply", LLMat_matrixmultiply, METH_VARARGS, "matrixmultiply(A, B)\n\nReturns a new ll_mat object representing the matrix A*B"},
+  {"dot", LLMat_dot, METH_VARARGS, "dot(A, B)\n\nReturns a new ll_mat object representing the matrix transpose(A)*B"},
+  {"symdot", LLMat_symdot, METH_VARARGS, "symdot(A) or symdot(A, d)\n\nReturns a new symmetric ll_mat object representing transpose(A)*A, or transpose(A)*diag(d)*A"},
   {"csr_from_arrays", csr_from_arrays, METH_VARARGS, "csr_from_arrays(m, n, ind, col, val) -> csr_mat (pysparse_b200 addition)"},
   {"sss_from_arrays", sss_from_arrays, METH_VARARGS, "sss_from_arrays(n, ind, col, val, diag) -> sss_mat (pysparse_b200 addition)"},
   {NULL, NULL}

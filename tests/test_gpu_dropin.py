@@ -171,3 +171,99 @@ def test_llmat_device_cache_tracks_modifications(mods):
     assert y2[0] == y1[0] + 6.0 * x[0] and np.array_equal(y1[1:], y2[1:])
     yt = np.empty(36); L.matvec_transp(x, yt)
     assert np.allclose(yt, y2)
+
+
+def _dense(A):
+    D = np.zeros(A.shape)
+    v, i, j = A.find()
+    D[i, j] = v
+    if A.issym:
+        D[j, i] = v
+    return D
+
+
+def test_edited_llmat_feeds_the_gpu_path(mods):
+    """Matrices produced by the assembly operations of SURVEY 8(f) -- fancy indexing, block
+    assignment, masks, scaling, row / column deletion -- multiply on the GPU like any other:
+    y = A x against the dense model (relative max-norm 1e-13), after EVERY modification (the
+    device copy must follow the container)."""
+    spmatrix, krylov, precon, poisson = mods
+    rng = np.random.default_rng(4)
+    A = poisson.poisson2d(8)                                  # 64 x 64 general
+
+    def check(M):
+        D = _dense(M)
+        m, n = M.shape
+        x = rng.standard_normal(n); y = np.full(m, np.nan)
+        M.matvec(x, y)
+        assert np.max(np.abs(y - D @ x)) <= 1e-13 * max(1.0, np.max(np.abs(D @ x)))
+        if not M.issym:
+            xt = rng.standard_normal(m); yt = np.full(n, np.nan)
+            M.matvec_transp(xt, yt)
+            assert np.max(np.abs(yt - D.T @ xt)) <= 1e-13 * max(1.0, np.max(np.abs(D.T @ xt)))
+
+    check(A)
+    B = A[::2, 5:40]                                          # 32 x 35 rectangular sub-matrix
+    check(B)
+    B.col_scale(rng.standard_normal(35)); check(B)
+    B.row_scale(rng.standard_normal(32)); check(B)
+    mask = np.ones(35, dtype=int); mask[3:9] = 0
+    B.delete_cols(mask); check(B)
+    mask = np.ones(32, dtype=int); mask[::5] = 0
+    B.delete_rows(mask); check(B)
+    A[8:16, 8:16] = A[0:8, 0:8]; check(A)
+    A[[1, 3, 5], :] = 0.0; check(A)
+    A.update_add_mask(rng.standard_normal((3, 3)), [0, 9, 63], [2, 9, 40], [1, 1, 1], [1, 0, 1]); check(A)
+    S = poisson.poisson2d_sym(8)
+    check(S)
+    keep = np.ones(64, dtype=int); keep[10:20] = 0
+    S.delete_rowcols(keep); check(S)
+    El = rng.standard_normal((3, 3)); El = El + El.T
+    S.update_add_mask_sym(El, [0, 7, 30], [1, 1, 1]); check(S)
+    check(S[:, :])                                            # general copy of the symmetric matrix
+
+
+def test_matrixmultiply_identity_of_the_reference_test(mods):
+    """test/test_spmatrix.py:204-221: (A B) x == A (B x) within eps * n * m * k."""
+    spmatrix = mods[0]
+    import random
+    rnd = random.Random(1)
+    eps = 2.2204460492503131e-16
+    n, m, k = 30, 60, 30
+
+    def ll_mat_rand(r, c, density):
+        M = spmatrix.ll_mat(r, c, int(density * r * c))
+        for _ in range(int(density * r * c)):
+            M[rnd.randrange(r), rnd.randrange(c)] = rnd.random()
+        return M
+
+    rng = np.random.default_rng(2)
+    for _ in range(10):
+        A = ll_mat_rand(n, k, 0.9); B = ll_mat_rand(k, m, 0.4)
+        C = spmatrix.matrixmultiply(A, B)
+        t = np.zeros(k); y1 = np.zeros(n); y2 = np.zeros(n)
+        for _ in range(3):
+            x = rng.random(m)
+            C.matvec(x, y1); B.matvec(x, t); A.matvec(t, y2)
+            assert np.sqrt(np.dot(y1 - y2, y1 - y2)) < eps * n * m * k
+
+
+def test_pysparse_matrix_operators(mods):
+    """PysparseMatrix: A * x, x * A (numpy defers to __rmul__), (A * B) * x, solver wrappers."""
+    from pysparse.sparse import PysparseMatrix, PysparseIdentityMatrix
+    from pysparse.itsolvers import krylov
+    L1 = PysparseMatrix(size=3)
+    L1.put([3., 10., np.pi, 2.5], [0, 0, 1, 2], [2, 1, 1, 0])
+    assert np.allclose(L1 * np.array((1, 2, 3), "d"), np.array((29., 6.28318531, 2.5)))      # pysparseMatrix.py:246-248
+    assert np.allclose(np.array((1, 2, 3), "d") * L1, np.array((7.5, 16.28318531, 3.)))      # :252-254
+    assert np.allclose(L1.matvec(np.ones(3)), L1.getNumpyArray() @ np.ones(3))
+    n = 12
+    P = PysparseMatrix(matrix=mods[3].poisson2d_sym(n))
+    x = np.random.default_rng(0).standard_normal(n * n)
+    y = P * x
+    y2 = (P + PysparseIdentityMatrix(size=n * n)) * x
+    assert np.allclose(y2, y + x, rtol=0, atol=1e-13)
+    assert np.allclose((2 * P) * x, 2 * y, rtol=0, atol=1e-12)
+    xs = np.zeros(n * n)
+    info, it, relres = krylov.pcg(P.getMatrix().to_sss(), y, xs, 1e-12, 1000)
+    assert info == 0 and np.max(np.abs(xs - x)) <= 1e-8

@@ -1,0 +1,128 @@
+"""CPU tests of the PysparseMatrix wrapper layer: the worked
+examples of the reference's docstrings (pysparse/sparse/pysparseMatrix.py:167-456, rendered in
+doc/pysparse/source/pysparsematrix.rst) as doctests, the sparse x sparse products of the
+container against dense NumPy, and the reference's test/test_spmatrix.py:204-221 product
+identity (the matvec legs of that test need the GPU and live in the GPU suite)."""
+import doctest
+
+import numpy as np
+import pytest
+
+
+@pytest.fixture(scope="module")
+def sp(native):
+    from pysparse.sparse import spmatrix
+    return spmatrix
+
+
+def test_docstring_examples(native):
+    from pysparse.sparse import pysparseMatrix
+    res = doctest.testmod(pysparseMatrix, optionflags=doctest.NORMALIZE_WHITESPACE)
+    assert res.attempted >= 25 and res.failed == 0
+
+
+def test_wrapper_surface_and_arithmetic(native):
+    from pysparse.sparse import PysparseMatrix, PysparseIdentityMatrix, PysparseSpDiagsMatrix
+    from pysparse.sparse.pysparseMatrix import PysparseMatrix as P2
+    assert P2 is PysparseMatrix
+    L = PysparseMatrix(size=3)
+    L.put([3., 10., np.pi, 2.5], [0, 0, 1, 2], [2, 1, 1, 0])
+    D = np.array([[0, 10, 3], [0, np.pi, 0], [2.5, 0, 0]])
+    assert L.shape == (3, 3) and L.nnz == 4 and not L.isSymmetric()
+    assert np.array_equal(L.getNumpyArray(), D)
+    I = PysparseIdentityMatrix(size=3)
+    assert I.isSymmetric() and np.array_equal((L + I).getNumpyArray(), D + np.eye(3))
+    assert np.array_equal((I + L).getNumpyArray(), D + np.eye(3))          # symmetric + general generalizes
+    assert np.array_equal((L - I).getNumpyArray(), D - np.eye(3))
+    assert (L + 0) is L and np.array_equal((L + 3).getNumpyArray(), np.where(D != 0, D + 3, 0))
+    assert np.array_equal((L * 2).getNumpyArray(), 2 * D) and np.array_equal((2 * L).getNumpyArray(), 2 * D)
+    assert np.array_equal((-L).getNumpyArray(), -D)
+    M = L.copy(); M += I; M -= L
+    assert np.array_equal(M.getNumpyArray(), np.eye(3))
+    M *= 4
+    assert np.array_equal(M.takeDiagonal(), 4 * np.ones(3))
+    with pytest.raises(TypeError):
+        L + PysparseMatrix(size=4)
+    with pytest.raises(TypeError):
+        L * PysparseMatrix(size=4)
+    with pytest.raises(TypeError):
+        M *= L
+    with pytest.raises(ValueError):
+        PysparseMatrix(size=3, nrow=4, ncol=3)
+    sub = L[:2, 1:]
+    assert isinstance(sub, PysparseMatrix) and np.array_equal(sub.getNumpyArray(), D[:2, 1:]) and L[0, 1] == 10.0
+    L[1:, 1:] = PysparseIdentityMatrix(size=2)
+    D[1:, 1:] = np.eye(2)
+    assert np.array_equal(L.getNumpyArray(), D)
+    L.addAtDiagonal(1.5); D += 1.5 * np.eye(3)
+    L.addAtDiagonal([1.0, 2.0]); D[0, 0] += 1.0; D[1, 1] += 2.0
+    assert np.array_equal(L.getNumpyArray(), D)
+    e = np.ones(5)
+    T = PysparseSpDiagsMatrix(size=5, vals=(-2 * e, e, 2 * e), pos=(-1, 0, 1))
+    assert np.array_equal(T.getNumpyArray(), np.diag(e) + np.diag(2 * e[:4], 1) + np.diag(-2 * e[:4], -1))
+    Ts = PysparseSpDiagsMatrix(size=5, vals=(-2 * e, e, 2 * e), pos=(-1, 0, 1), symmetric=True)
+    assert Ts.isSymmetric() and Ts.nnz == 9 and Ts[0, 1] == -2.0
+    R = PysparseMatrix(nrow=2, ncol=4)
+    assert R.shape == (2, 4)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_container_products_vs_dense(sp, seed):
+    rng = np.random.default_rng(seed)
+    n, k, m = int(rng.integers(3, 12)), int(rng.integers(3, 12)), int(rng.integers(3, 12))
+
+    def rand(r, c, dens):
+        D = rng.standard_normal((r, c)) * (rng.random((r, c)) < dens)
+        A = sp.ll_mat(r, c)
+        for i in range(r):
+            for j in range(c):
+                if D[i, j]:
+                    A[i, j] = D[i, j]
+        return A, D
+
+    def dense(A):
+        D = np.zeros(A.shape); v, i, j = A.find(); D[i, j] = v
+        if A.issym:
+            D[j, i] = v
+        return D
+
+    A, Da = rand(n, k, 0.6); B, Db = rand(k, m, 0.5)
+    C = sp.matrixmultiply(A, B)
+    assert C.shape == (n, m) and not C.issym and np.allclose(dense(C), Da @ Db, rtol=0, atol=1e-13)
+    # bit-exact against the reference's accumulation order: terms added in ascending k
+    exp = np.zeros((n, m))
+    for i in range(n):
+        for kk in range(k):
+            if Da[i, kk]:
+                for j in range(m):
+                    if Db[kk, j]:
+                        exp[i, j] += Da[i, kk] * Db[kk, j]
+    assert np.array_equal(dense(C), exp)
+    B2, Db2 = rand(n, m, 0.5)
+    assert np.allclose(dense(sp.dot(A, B2)), Da.T @ Db2, rtol=0, atol=1e-13)
+    S = sp.symdot(A)
+    assert S.issym and S.shape == (k, k) and np.allclose(dense(S), Da.T @ Da, rtol=0, atol=1e-13)
+    d = rng.standard_normal(n)
+    assert np.allclose(dense(sp.symdot(A, d)), Da.T @ np.diag(d) @ Da, rtol=0, atol=1e-13)
+    # symmetric x general
+    Ds = rng.standard_normal((k, k)) * (rng.random((k, k)) < 0.5); Ds = np.tril(Ds) + np.tril(Ds, -1).T
+    Ssym = sp.ll_mat_sym(k)
+    for i in range(k):
+        for j in range(i + 1):
+            if Ds[i, j]:
+                Ssym[i, j] = Ds[i, j]
+    assert np.allclose(dense(sp.matrixmultiply(Ssym, B)), Ds @ Db, rtol=0, atol=1e-13)
+    with pytest.raises(NotImplementedError):
+        sp.matrixmultiply(A, Ssym)                       # general x symmetric: as the reference
+    with pytest.raises(NotImplementedError):
+        sp.matrixmultiply(Ssym, Ssym)
+    with pytest.raises(NotImplementedError):
+        sp.dot(Ssym, Ssym)
+    with pytest.raises(NotImplementedError):
+        sp.symdot(Ssym)
+    with pytest.raises(ValueError):
+        sp.matrixmultiply(A, sp.ll_mat(k + 1, m))
+    with pytest.raises(ValueError):
+        sp.dot(A, sp.ll_mat(n + 1, m))
+    with pytest.raises(sp.error):
+        sp.symdot(A, np.ones(n + 1))
