@@ -1,29 +1,32 @@
 """Object-oriented front end to the Krylov solvers.
 
-Python-3 restatement of ``pysparse/itsolvers/itsolvers_util.py:13-125``: same
-class names, same ``solve(rhs, x, tol, maxit)`` protocol (x is zeroed first,
-``info < 0`` is recorded, not raised unless ``debug``), same attributes
-(``nofCalled``, ``totalIterations``, ``lastIterations``, ``lastInfo``,
-``itn``, ``resNorm``, ``converged``).
+Python-3 restatement of ``pysparse/itsolvers/itsolvers_util.py:13-152``: same class names,
+``Solver(A, debug=False)`` construction (``A`` an ``ll_mat`` / ``csr_mat`` / ``sss_mat`` or a
+``PysparseMatrix``, which is unwrapped), ``solve(b, x, tol, maxit, K=None)`` with a zero
+initial guess, the counters ``nofCalled``, ``totalIterations``, ``lastIterations``,
+``lastInfo``, and -- as in the reference -- a ``RuntimeError`` carrying ``(message, info,
+iter, relres)`` when the solver reports ``info < 0``.  Additions that do not change that
+protocol: a ``precon=`` keyword at construction (default ``K`` of ``solve``), the attributes
+``itn``, ``resNorm``, ``converged``, and ``solve`` returns ``(info, iter, relres)``.
 """
-import numpy as np
-
 from . import krylov
 
-__all__ = ["ItSolver", "Pcg", "Minres", "Qmrs", "Cgs", "Bicgstab", "Gmres"]
+__all__ = ["ItSolver", "Pcg", "Minres", "Qmrs", "Cgs", "Bicgstab", "Gmres",
+           "pcg", "minres", "qmrs", "cgs", "bicgstab", "gmres"]
 
 
 class ItSolver:
-    """Abstract base class of the iterative solvers."""
+    "Abstract base class for iterative solver classes."
 
     itsolver = None
     name = "Generic"
 
-    def __init__(self, matrix, **kwargs):
-        self.matrix = matrix
-        self.type = self.name
+    def __init__(self, A, debug=False, **kwargs):
+        from ..sparse.pysparseMatrix import PysparseMatrix
+        self.A = A.matrix if isinstance(A, PysparseMatrix) else A
+        self.matrix = self.A
         self.precon = kwargs.get("precon", None)
-        self.debug = kwargs.get("debug", False)
+        self.debug = debug
         self.nofCalled = 0
         self.totalIterations = 0
         self.lastIterations = 0
@@ -32,32 +35,43 @@ class ItSolver:
         self.resNorm = 0.0
         self.converged = False
 
-    def solve(self, rhs, x, tol, maxit, K=None):
-        """Solve A x = rhs to relative tolerance ``tol`` in at most ``maxit`` iterations."""
-        if self.itsolver is None:
-            raise NotImplementedError("ItSolver is an abstract class")
+    def set_name(self, name):
+        self.name = name
+
+    def set_solver(self, solver):
+        self.itsolver = solver
+
+    def solve(self, b, x, tol, maxit, K=None):
+        "Solve Ax = b iteratively with zero initial guess"
+        if not self.itsolver:
+            raise NotImplementedError("This class cannot be used directly.")
         if K is None:
             K = self.precon
-        x[:] = 0.0
-        if K is None:
-            info, it, relres = self.itsolver(self.matrix, rhs, x, tol, maxit)
-        else:
-            info, it, relres = self.itsolver(self.matrix, rhs, x, tol, maxit, K)
+        x[:] = 0
+        info, it, relres = self.itsolver(self.A, b, x, tol, maxit, K)
         self.nofCalled += 1
         self.totalIterations += it
         self.lastIterations = self.itn = it
         self.lastInfo = info
         self.resNorm = relres
         self.converged = info >= 0
-        if info < 0 and self.debug:
-            raise RuntimeError("%s: info = %d after %d iterations (relres %g)" % (self.name, info, it, relres))
+        if self.debug:
+            print("iterative solver returned:", info, it, relres)
+        if info < 0:
+            raise RuntimeError("iterative solver %s returned error code %d" % (self.__class__.__name__, info),
+                               info, it, relres)
         return info, it, relres
 
     def __call__(self, *args, **kwargs):
         return self.solve(*args, **kwargs)
 
-    def __repr__(self):
-        return "<%s solver, called %d times, %d iterations>" % (self.name, self.nofCalled, self.totalIterations)
+    def __str__(self):
+        s = "<%s.%s instance>\n\n" % (self.__class__.__module__, self.__class__.__name__)
+        for name in ("nofCalled", "totalIterations", "lastIterations", "lastInfo"):
+            s += "   %s: %s\n" % (name, getattr(self, name))
+        return s + "\n"
+
+    __repr__ = __str__
 
 
 class Pcg(ItSolver):
@@ -88,3 +102,29 @@ class Bicgstab(ItSolver):
 class Gmres(ItSolver):
     name = "Gmres"
     itsolver = staticmethod(krylov.gmres)
+
+
+# module-level functions of the reference (itsolvers_util.py:128-152; deprecated there in
+# favour of the classes): plain pass-throughs to the krylov module
+def pcg(*args, **kwargs):
+    return krylov.pcg(*args, **kwargs)
+
+
+def minres(*args, **kwargs):
+    return krylov.minres(*args, **kwargs)
+
+
+def qmrs(*args, **kwargs):
+    return krylov.qmrs(*args, **kwargs)
+
+
+def cgs(*args, **kwargs):
+    return krylov.cgs(*args, **kwargs)
+
+
+def bicgstab(*args, **kwargs):
+    return krylov.bicgstab(*args, **kwargs)
+
+
+def gmres(*args, **kwargs):
+    return krylov.gmres(*args, **kwargs)

@@ -113,3 +113,33 @@ def poisson2d_sym_vec(n):
     L.put(-np.ones(len(inner)), inner, inner - 1)
     L.put(-e[n:], d[n:], d[:-n])
     return L
+
+
+def poisson1d_sym_vec(n):
+    L = spmatrix.ll_mat_sym(n, 2 * n - 1)
+    e = np.ones(n)
+    d = np.arange(n, dtype=np.int64)
+    L.put(2 * e, d, d)
+    L.put(-e[1:], d[1:], d[:-1])
+    return L
+
+
+def poisson2d_vec2(n):
+    "Same matrix as :func:`poisson2d_vec` (the reference keeps two vectorised variants)."
+    return poisson2d_vec(n)
+
+
+def poisson2d_sym_blk_vec(n):
+    "Block assembly with vectorised blocks: diagonal blocks D, sub-diagonal blocks -I."
+    n2 = n * n
+    L = spmatrix.ll_mat_sym(n2, 3 * n2 - 2 * n)
+    D = poisson1d_sym_vec(n)
+    d = np.arange(n, dtype=np.int64)
+    D.put(4 * np.ones(n), d, d)
+    P = spmatrix.ll_mat(n, n, n)
+    P.put(-np.ones(n), d, d)
+    for i in range(n - 1):
+        L[i * n:(i + 1) * n, i * n:(i + 1) * n] = D
+        L[(i + 1) * n:(i + 2) * n, i * n:(i + 1) * n] = P
+    L[n2 - n:n2, n2 - n:n2] = D
+    return L

@@ -77,6 +77,13 @@ def test_all_solvers_oo_wrappers(mods):
             assert info == 0 and s.converged and s.itn == it and s.nofCalled == 1
             r = np.empty(n); A.matvec(x, r)
             assert np.linalg.norm(b - r) <= 2e-7 * np.linalg.norm(b), (cls.name, K)
+    # info < 0 raises, with (message, info, iter, relres) as arguments (itsolvers_util.py:47-48)
+    from pysparse.sparse import PysparseMatrix
+    s = its.Pcg(PysparseMatrix(matrix=L))          # a PysparseMatrix is unwrapped (:19-22)
+    with pytest.raises(RuntimeError) as ei:
+        s.solve(b, np.zeros(n), 1e-12, 5)
+    assert ei.value.args[1] == -1 and s.lastInfo == -1 and s.nofCalled == 1 and not s.converged
+    assert "nofCalled: 1" in str(s)
 
 
 def test_x_updated_in_place_only_when_contiguous_float64(mods):

@@ -126,3 +126,46 @@ def test_container_products_vs_dense(sp, seed):
         sp.dot(A, sp.ll_mat(n + 1, m))
     with pytest.raises(sp.error):
         sp.symdot(A, np.ones(n + 1))
+
+
+def test_tools_and_solver_wrapper_surface(native, capsys):
+    """tools.poisson_vec builds the same matrices as tools.poisson (reference:
+    examples/poisson_test_vec.py compares them the same way); spmatrix_util helpers; the
+    itsolvers_util classes and pass-through functions exist with the reference's protocol."""
+    from pysparse.sparse import spmatrix
+    from pysparse.tools import poisson, poisson_vec, spmatrix_util, sptime
+    import pysparse.itsolvers.itsolvers_util as iu
+    from pysparse.itsolvers import krylov
+
+    def same(a, b):
+        z = a.copy(); z.shift(-1.0, b)
+        return z.nnz == 0 and a.shape == b.shape and a.issym == b.issym and a.nnz == b.nnz
+
+    n = 7
+    assert same(poisson.poisson1d(n), poisson_vec.poisson1d_vec(n))
+    assert same(poisson.poisson1d_sym(n), poisson_vec.poisson1d_sym_vec(n))
+    assert same(poisson.poisson2d(n), poisson_vec.poisson2d_vec(n)) and same(poisson.poisson2d(n), poisson_vec.poisson2d_vec2(n))
+    assert same(poisson.poisson2d_sym(n), poisson_vec.poisson2d_sym_vec(n))
+    assert same(poisson.poisson2d_sym_blk(n), poisson_vec.poisson2d_sym_blk_vec(n))
+    assert same(poisson.poisson2d_sym(n), poisson_vec.poisson2d_sym_blk_vec(n))
+    assert spmatrix_util.bytesToString(100) == "100 Bytes" and spmatrix_util.bytesToString(2048) == "2.0 Kbytes"
+    assert spmatrix_util.bytesToString(3 * 1024 ** 2) == "3.0 Mbytes" and spmatrix_util.bytesToString(5 * 1024 ** 3) == "5.0 Gbytes"
+    L = poisson.poisson2d_sym(n)
+    spmatrix_util.printInfo(L, "L"); spmatrix_util.printInfo(L.to_sss(), "S"); spmatrix_util.printInfo(L.to_csr(), "A")
+    out = capsys.readouterr().out
+    assert "LL symmetric" in out and "SSS" in out and "CSR" in out and "%dx%d" % (n * n, n * n) in out
+    # storage formulas of SURVEY section 8: CSR = 4 N + 12 nnz, SSS = 12 N + 12 nnz_lower
+    A = L.to_csr(); S = L.to_sss()
+    assert spmatrix_util.storage_bytes(A) == 4 * n * n + 12 * A.nnz
+    assert spmatrix_util.storage_bytes(S) == 12 * n * n + 12 * (S.nnz - n * n)
+    R = spmatrix_util.ll_mat_rand(10, 12, 0.2)
+    assert R.shape == (10, 12) and 0 < R.nnz <= 24
+    assert sptime.cputime() >= 0.0
+    for cls, fn in ((iu.Pcg, krylov.pcg), (iu.Minres, krylov.minres), (iu.Qmrs, krylov.qmrs), (iu.Cgs, krylov.cgs),
+                    (iu.Bicgstab, krylov.bicgstab), (iu.Gmres, krylov.gmres)):
+        s = cls(L)
+        assert s.itsolver is fn and s.A is L and s.nofCalled == 0 and not s.debug and callable(s)
+    with pytest.raises(NotImplementedError):
+        iu.ItSolver(L, False).solve(np.ones(n * n), np.zeros(n * n), 1e-8, 10)
+    for name in ("pcg", "minres", "qmrs", "cgs", "bicgstab", "gmres"):
+        assert callable(getattr(iu, name))
