@@ -218,7 +218,10 @@ int psp_dist_csr_create(const int *rowptr, int nnz, const int *ind, const int *c
 /* Optional send map (push model of the single-launch PCG kernel): entry s says that
  * local row rows[s] must be stored at element dst_off[s] of the multiplied vector in
  * rank dst_rank[s]'s heap (dst_off = that rank's local row count + its halo position).
- * Without it the halo is pulled by the consumer. */
+ * Without it the halo is pulled by the consumer.  The maps of all ranks together must
+ * cover every halo entry of every rank exactly once (the receiver waits for each of its
+ * halo entries); pysparse_b200/dist.py builds them by inverting the all-gathered halo
+ * lists of psp_dist_plan.  Call after psp_dist_connect. */
 int psp_dist_set_sendmap(psp_dmat *a, int nsend, const int *rows, const int *dst_rank,
                          const int *dst_off);
 void psp_dist_mat_destroy(psp_dmat *a);

@@ -232,14 +232,12 @@ extern "C" int psp_dist_set_sendmap(psp_dmat *m, int nsend, const int *rows, con
     set_error("psp_dist_set_sendmap: bad arguments");
     return PSP_ERR_ARG;
   }
-  unsigned mask = 0;
   for (int s = 0; s < nsend; s++) {
     if (rows[s] < 0 || rows[s] >= dm->nl || dst_rank[s] < 0 || dst_rank[s] >= d.world || dst_rank[s] == d.rank ||
         dst_off[s] < 0 || (size_t)dst_off[s] >= d.slot_elems) {
       set_error("psp_dist_set_sendmap: entry %d out of range", s);
       return PSP_ERR_ARG;
     }
-    mask |= 1u << dst_rank[s];
   }
   if (!d.ready) { set_error("psp_dist_set_sendmap: distributed layer not connected"); return PSP_ERR_DIST; }
   cudaFree(dm->d_send_row); cudaFree(dm->d_send_dst);
@@ -261,7 +259,6 @@ extern "C" int psp_dist_set_sendmap(psp_dmat *m, int nsend, const int *rows, con
     PSP_CUDA(cudaMemcpy(dm->d_send_dst, dst.data(), sizeof(unsigned long long *) * (size_t)nsend, cudaMemcpyHostToDevice));
   }
   dm->nsend = nsend;
-  dm->sendmask = mask;
   dm->has_sendmap = true;
   return PSP_OK;
 }

@@ -25,7 +25,6 @@ struct DistMat {
   int nsend = 0;
   int *d_send_row = nullptr;
   unsigned long long **d_send_dst = nullptr;   // landing-zone address of each entry in the neighbour's heap
-  unsigned sendmask = 0;                  // ranks this rank pushes halo values to
   bool has_sendmap = false;
 };
 

@@ -5,16 +5,22 @@
 // common case (native matrix, identity or single-step Jacobi preconditioner):
 // one launch per solve, the iteration loop, the reductions and the convergence
 // test (pcg.c:91-165) all run on the device; the host is not involved until
-// the kernel ends.  Per iteration the grid passes three barriers (after the
-// p update, after the SpMV partial sums, after the x/r update partial sums)
-// instead of three kernel boundaries; every CTA reduces the per-CTA partials
-// redundantly in the same order, so all CTAs -- and, multi-GPU, all ranks --
-// take bit-identical decisions.  The matrix slices of the NEXT SpMV pass are
-// prefetched into the TMA ring while the vector phases run.
+// the kernel ends.  Per iteration the grid synchronises three times (after the
+// p update, with the SpMV partial sums, with the x/r update partial sums)
+// instead of crossing three kernel boundaries.  The two reductions ARE the
+// barriers: every CTA deposits its partial sums and draws a ticket, the CTA
+// with the last ticket adds the partials in index order, publishes the totals
+// and releases the others -- all CTAs, and multi-GPU all ranks, see the same
+// bits and take identical decisions.  The matrix slices of the NEXT SpMV pass
+// are prefetched into the TMA ring while the vector phases run.
 //
-// Multi-GPU: the halo of p is pulled from the neighbours' heaps between the p
-// update and the SpMV (publish / poll as in psp_dist.cu) and the scalar
-// all-reduces go through the peer mailboxes from inside the kernel.
+// Multi-GPU (row slabs, one process per GPU): the boundary entries of the new
+// search direction are pushed into the neighbours' landing zones as
+// self-validating words at the start of the p update and unpacked after the
+// barrier, the row blocks that read halo columns run last (push model; the
+// pull model of psp_dist.cu is the fallback without a send map); the scalar
+// all-reduces go through the peer mailboxes from inside the reduction, one
+// NVLink trip each.  No system-scope fences, no collective library.
 //
 // The scalar logic is NOT duplicated: thread 0 of every CTA runs the same
 // run_epilogue() cases as the multi-kernel path on a shared-memory copy of the
@@ -64,7 +70,6 @@ struct PcgArgs {
   int push, nsend;
   const int *send_row;
   unsigned long long *const *send_dst;    // per entry: its two words in the neighbour's landing zone
-  unsigned sendmask;
 };
 
 struct PersistSync {            // global scratch of the all-reduce / barrier (zeroed before each launch)
@@ -565,7 +570,7 @@ int pcg_persist_launch(const psp_mat *M, int n, const double *b, double *x, doub
   a.halo_owner = dm ? dm->d_owner : nullptr; a.halo_ridx = dm ? dm->d_ridx : nullptr;
   a.nhalo = dm ? dm->nhalo : 0; a.nbmask = dm ? dm->nbmask : 0u;
   a.push = (dm && dm->has_sendmap && c.dist_push) ? 1 : 0;
-  a.nsend = dm ? dm->nsend : 0; a.sendmask = dm ? dm->sendmask : 0u;
+  a.nsend = dm ? dm->nsend : 0;
   a.send_row = dm ? dm->d_send_row : nullptr; a.send_dst = dm ? dm->d_send_dst : nullptr;
   size_t p_slot_off = dm ? (size_t)(p - dist().heap) : 0;
   // enough CTAs for the vector phases and the row blocks, never more than are co-resident
