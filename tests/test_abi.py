@@ -51,3 +51,30 @@ def test_oracle_is_not_imported_by_the_product():
             if f.endswith((".py", ".c", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "import oracle" not in src and "from oracle" not in src and "psp_oracle" not in src, f
+
+
+def test_hot_kernels_keep_their_register_budget(native):
+    """The persistent PCG kernel runs at 64 registers (4 CTAs per SM).  When ptxas had to spill
+    ~200 bytes per thread into its loops it was 12 % slower (621 vs 550 us per iteration at
+    256^3) -- slower than the per-phase path it replaces -- so a change that brings the spills
+    back must fail here, not show up as a benchmark regression.  The SpMV kernels must not
+    spill at all."""
+    out = subprocess.run(["cuobjdump", "-res-usage", native.LIB_PATH], capture_output=True, text=True).stdout
+    usage = {}
+    name = None
+    for line in out.splitlines():
+        m = re.search(r"Function (\S+):", line)
+        if m:
+            name = m.group(1)
+            continue
+        m = re.search(r"REG:(\d+) STACK:(\d+)", line)
+        if m and name:
+            usage[name] = (int(m.group(1)), int(m.group(2)))
+    persist = [v for k, v in usage.items() if "k_pcg_persist" in k]
+    assert persist, "k_pcg_persist not found in the library"
+    for reg, stack in persist:
+        assert reg <= 64 and stack <= 32, (reg, stack)
+    spmv = [v for k, v in usage.items() if "k_spmv_tma" in k]
+    assert len(spmv) >= 2
+    for reg, stack in spmv:
+        assert reg <= 64 and stack == 0, (reg, stack)
