@@ -13,7 +13,7 @@ import pysparse_b200
 __version__ = pysparse_b200.__version__
 
 for _name in ("sparse", "sparse.spmatrix", "sparse.pysparseMatrix", "sparse.sparseMatrix", "itsolvers", "itsolvers.krylov", "itsolvers.itsolvers_util",
-              "precon", "precon.precon", "tools", "tools.poisson", "tools.poisson_vec", "tools.spmatrix_util",
+              "precon", "precon.precon", "eigen", "eigen.jdsym", "tools", "tools.poisson", "tools.poisson_vec", "tools.spmatrix_util",
               "tools.sptime", "tools.gallery"):
     _mod = importlib.import_module("pysparse_b200." + _name)
     sys.modules["pysparse." + _name] = _mod

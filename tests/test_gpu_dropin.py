@@ -274,3 +274,58 @@ def test_pysparse_matrix_operators(mods):
     xs = np.zeros(n * n)
     info, it, relres = krylov.pcg(P.getMatrix().to_sss(), y, xs, 1e-12, 1000)
     assert info == 0 and np.max(np.abs(xs - x)) <= 1e-8
+
+
+def test_jdsym_reference_cases_on_the_gpu_path(mods):
+    """test/test_jdsym.py:10-16 and examples/jdsym_test.py:36-117 with the real pieces: sss_mat
+    products, krylov.qmrs as the inner solver and the correction equation passed to it as a
+    duck-typed operator (whose matvec calls back into the GPU products)."""
+    spmatrix, krylov, precon, poisson = mods
+    from pysparse.eigen import jdsym
+    a = spmatrix.ll_mat(3, 3)
+    a.put([1, 2, 3])
+    r = jdsym.jdsym(a, None, None, 3, 1, 1e-9, 100, krylov.qmrs)
+    assert r[0] == 3 and np.allclose(r[1], [1, 2, 3]) and np.allclose(np.abs(r[2]), np.identity(3))
+
+    n, ncv, tol = 1000, 5, 1e-6
+    A = spmatrix.ll_mat_sym(n); M = spmatrix.ll_mat_sym(n)
+    d = np.arange(n)
+    A.put(d + 1.0, d, d); M.put(float(n // 2) + d, d, d)
+    As, Ms = A.to_sss(), M.to_sss()
+    normM = M[n - 1, n - 1]
+
+    class DiagPrecShifted:                       # examples/jdsym_test.py:7-15
+        shape = (n, n)
+        dinv = 1.0 / ((d + 1.0) - 0.006 * (float(n // 2) + d))
+
+        def precon(self, x, y):
+            np.multiply(x, self.dinv, y)
+
+    def residuals(Aop, Mop, lam, Q):
+        out = np.zeros(len(lam))
+        for k in range(len(lam)):
+            u = Q[:, k].copy(); rr = np.zeros(n); t = np.zeros(n)
+            Aop.matvec(u, rr)
+            if Mop is not None:
+                Mop.matvec(u, t)
+            else:
+                t = u
+            out[k] = np.linalg.norm(rr - lam[k] * t)
+        return out
+
+    kw = dict(jmin=5, jmax=10, eps_tr=1e-4)
+    kconv, lam, Q, it, it_inner = jdsym.jdsym(As, None, None, ncv, 0.0, tol, 150, krylov.qmrs, **kw)
+    assert kconv == ncv and np.all(residuals(As, None, lam, Q) <= tol)
+    assert np.allclose(lam, d[:ncv] + 1.0, rtol=tol * tol, atol=1e-9)
+    exact = ((d + 1.0) / (float(n // 2) + d))[:ncv]
+    for K in (None, DiagPrecShifted()):
+        kconv, lam, Q, it, it_inner = jdsym.jdsym(As, Ms, K, ncv, 0.0, tol, 150, krylov.qmrs, **kw)
+        assert kconv == ncv and np.all(residuals(As, Ms, lam, Q) <= normM * tol)
+        assert np.allclose(np.sort(lam), exact, rtol=0, atol=normM * tol * tol + 1e-9)
+    # a native preconditioner object and a 2-D Poisson spectrum
+    L = poisson.poisson2d_sym(12)
+    S = L.to_sss()
+    kconv, lam, Q, it, _ = jdsym.jdsym(S, None, precon.jacobi(L), 4, 0.0, 1e-8, 200, krylov.qmrs)
+    T = 2 * np.eye(12) - np.eye(12, k=1) - np.eye(12, k=-1)
+    w = np.linalg.eigvalsh(np.kron(np.eye(12), T) + np.kron(T, np.eye(12)))
+    assert kconv == 4 and np.allclose(np.sort(lam), w[:4], rtol=0, atol=1e-7)
