@@ -1,6 +1,9 @@
 """Five smallest eigenpairs of the 2-D Poisson matrix with JDSYM, QMRS as the inner solver and a
 Jacobi preconditioner (the call pattern of the reference's doc/pysparse/source/jdsym.rst example
 and examples/jdsym_test.py)."""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))   # run from the source tree
+
 import numpy as np
 
 from pysparse.eigen import jdsym

@@ -5,6 +5,9 @@
 Every rank assembles only its own slab of rows (whole grid planes), the halo exchange and the
 scalar all-reduces are done by the solver kernel over NVLink peer memory; torch.distributed is
 used for the rendezvous only."""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))   # run from the source tree
+
 import os
 import sys
 

@@ -1,5 +1,8 @@
 """2-D Poisson problem solved with PCG on the three matrix formats, with and without SSOR
 (the flow of the reference's examples/poisson_test.py:62-135)."""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))   # run from the source tree
+
 import sys
 import time
 
