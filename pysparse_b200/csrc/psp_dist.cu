@@ -105,6 +105,13 @@ extern "C" int psp_dist_plan(int world, int rank, const int *rowptr, int nl, con
 }
 
 // ------------------------------------------------------------------ symmetric heap / IPC
+// First element of the halo landing zone: after the work vectors, rounded up to an even
+// element so that every (2e, 2e+1) word pair is 16-byte aligned (it is read with one
+// 16-byte load).
+static size_t ll_offset(size_t slot_elems, int nslots) {
+  return (slot_elems * (size_t)nslots + 1) & ~(size_t)1;
+}
+
 extern "C" int psp_dist_init(int rank, int world, size_t slot_elems, int nslots, void *handles_out) {
   if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world || !handles_out) {
     set_error("psp_dist_init: bad arguments (world must be 1..%d)", kMaxRanks);
@@ -116,7 +123,7 @@ extern "C" int psp_dist_init(int rank, int world, size_t slot_elems, int nslots,
   d.rank = rank; d.world = world; d.slot_elems = slot_elems; d.nslots = nslots;
   // nslots work vectors, then the flag-in-data halo landing zone of the persistent kernels:
   // two 8-byte words per vector element (see DistDev::ll_off)
-  const size_t heap_bytes = sizeof(double) * slot_elems * (size_t)(nslots + 2);
+  const size_t heap_bytes = sizeof(double) * (ll_offset(slot_elems, nslots) + 2 * slot_elems);
   PSP_CUDA(cudaMalloc((void **)&d.heap, heap_bytes ? heap_bytes : 8));
   PSP_CUDA(cudaMemset(d.heap, 0, heap_bytes ? heap_bytes : 8));
   PSP_CUDA(cudaMalloc((void **)&d.ctl, sizeof(DistCtl)));
@@ -135,7 +142,7 @@ extern "C" int psp_dist_connect(const void *all_handles) {
   DistDev dd;
   memset(&dd, 0, sizeof dd);
   dd.rank = d.rank; dd.world = d.world;
-  dd.ll_off = d.slot_elems * (size_t)d.nslots;
+  dd.ll_off = ll_offset(d.slot_elems, d.nslots);
   for (int w = 0; w < d.world; w++) {
     if (w == d.rank) { d.peer_heap[w] = d.heap; d.peer_ctl[w] = d.ctl; }
     else {
@@ -252,7 +259,7 @@ extern "C" int psp_dist_set_sendmap(psp_dmat *m, int nsend, const int *rows, con
   if (nsend) {
     // element e of the neighbour's vector <-> words 2e, 2e+1 of its landing zone
     std::vector<unsigned long long *> dst((size_t)nsend);
-    const size_t ll_off = d.slot_elems * (size_t)d.nslots;
+    const size_t ll_off = ll_offset(d.slot_elems, d.nslots);
     for (int s = 0; s < nsend; s++)
       dst[s] = reinterpret_cast<unsigned long long *>(d.peer_heap[dst_rank[s]] + ll_off) + 2 * (size_t)dst_off[s];
     PSP_CUDA(cudaMemcpy(dm->d_send_row, rows, sizeof(int) * (size_t)nsend, cudaMemcpyHostToDevice));
