@@ -148,6 +148,30 @@ for i in range(nl):
         s += fv[k] * x[fc[k]]
     yr[i] = s
 ok = bool(np.array_equal(y, yr))
+# push model: invert the all-gathered halo lists into send maps (what ShardedMatrix does) and
+# deliver every boundary entry to element dst_off of the neighbour's vector
+lists = [None] * world
+dist.all_gather_object(lists, (nl, ho, hr))
+rows, dst_rank, dst_off = D.build_sendmap(rank, lists)
+xpush = np.concatenate([xl, np.full(len(hg), np.nan)])
+recv = []
+for src in range(world):
+    if src == rank:
+        continue
+    cnt = int(np.sum(np.asarray(lists[rank][1]) == src))          # my halo entries owned by src
+    if cnt:
+        buf = torch.empty(2 * cnt, dtype=torch.float64)
+        recv.append((buf, dist.irecv(buf, src=src)))
+for dst in range(world):
+    sel = dst_rank == dst
+    if dst != rank and sel.any():
+        payload = np.concatenate([dst_off[sel].astype(np.float64), xl[rows[sel]]])   # (offsets, values)
+        dist.send(torch.from_numpy(payload), dst=dst)
+for buf, req in recv:
+    req.wait()
+    a = buf.numpy(); c = len(a) // 2
+    xpush[a[:c].astype(np.int64)] = a[c:]
+ok = ok and bool(np.array_equal(xpush, xfull))
 flags = [None] * world
 dist.all_gather_object(flags, ok)
 dist.destroy_process_group()
