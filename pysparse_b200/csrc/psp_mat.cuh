@@ -17,6 +17,7 @@ struct psp_mat {
   int nb = 0;
   int nint = 0;             // leading blocks that read no halo column (== nb unless sharded)
   int *d_blk = nullptr;
+  int *d_blk_halo = nullptr; // sharded slabs: per block, [first, end) of the halo positions it reads (int2)
   // SSS originals (strict lower CSR + diagonal), kept for the SSOR sweeps
   int *d_lind = nullptr, *d_lcol = nullptr;
   double *d_lval = nullptr, *d_diag = nullptr;

@@ -343,6 +343,29 @@ __device__ __forceinline__ void halo_unpack(PersistCtx &c, const PcgArgs &a, dou
   }
 }
 
+#ifdef PSP_BLOCK_UNPACK
+// Variant (A/B build -DPSP_BLOCK_UNPACK, not the default): no unpack pass and no tickets.
+// A boundary block's CTA unpacks, right before the block, exactly the halo positions that
+// block reads (MatView::blk_halo); ranges of different blocks may overlap, the CTAs then
+// write identical values.  Takes the unpack off the start of the SpMV pass.
+__device__ __forceinline__ void halo_unpack_block(PersistCtx &c, const PcgArgs &a, double *vec, int b) {
+  if (c.debug >= 1) return;
+  DistDev *dd = c.dd;
+  const int2 hr = __ldg(a.A.blk_halo + b);
+  const unsigned tag = c.pubs;
+  const unsigned long long *ll =
+      reinterpret_cast<const unsigned long long *>(dd->heap[dd->rank] + dd->ll_off) + 2 * (size_t)a.n;
+  for (int h = hr.x + (int)threadIdx.x; h < hr.y; h += (int)blockDim.x) {
+    unsigned long long w0, w1;
+    do {
+      asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(ll + 2 * (size_t)h) : "memory");
+    } while ((unsigned)(w0 >> 32) != tag || (unsigned)(w1 >> 32) != tag);
+    vec[a.n + h] = __longlong_as_double((long long)((w1 << 32) | (w0 & 0xffffffffull)));
+  }
+  __syncthreads();
+}
+#endif
+
 // before the first row block that reads a halo column
 __device__ __forceinline__ void halo_wait(PersistCtx &c, const PcgArgs &a) {
   if (c.debug >= 1) return;
@@ -398,12 +421,21 @@ __global__ void __launch_bounds__(kThreads, kPersistCtas) k_pcg_persist(PcgArgs 
       for (unsigned s = g0; s < (unsigned)a.nsend; s += gstride) halo_send(c, a, s, a.x[a.send_row[s]]);
     for (unsigned i = g0; i < n; i += gstride) p_cur[i] = a.x[i];
     grid.sync();
+#ifdef PSP_BLOCK_UNPACK
+    if (push) c.pubs += 1;
+#else
     if (push) halo_unpack(c, a, p_cur);
+#endif
     else publish_and_pull(grid, c, a, a.p, p_slot_off);
     xin = p_cur;
   }
+#ifdef PSP_BLOCK_UNPACK
+  ring.template pass<false, true>(a.A, xin, red_sh, [&](int r, double sum) { a.r[r] = sum; },
+                                  [&](int b) { if (push) halo_unpack_block(c, a, p_cur, b); });
+#else
   ring.template pass<false>(a.A, xin, red_sh, [&](int r, double sum) { a.r[r] = sum; },
-                            [&] { if (push) halo_wait(c, a); });
+                            [&](int) { if (push) halo_wait(c, a); });
+#endif
   ring.prefetch(a.A);
   grid.sync();
   {
@@ -463,14 +495,23 @@ __global__ void __launch_bounds__(kThreads, kPersistCtas) k_pcg_persist(PcgArgs 
     grid.sync();
     PROF_T(c, 1);
     if (c.dd) {
+#ifdef PSP_BLOCK_UNPACK
+      if (push) c.pubs += 1;
+#else
       if (push) halo_unpack(c, a, p_new);
+#endif
       else publish_and_pull(grid, c, a, a.p, p_slot_off);    // pull model: p is updated in place
     }
     PROF_T(c, 2);
     {                                   // q = A p ; pq = p.q
       double acc[1] = {0.0};
+#ifdef PSP_BLOCK_UNPACK
+      ring.template pass<false, true>(a.A, p_new, red_sh, [&](int r, double sum) { a.q[r] = sum; acc[0] += p_new[r] * sum; },
+                                      [&](int b) { if (push) halo_unpack_block(c, a, p_new, b); });
+#else
       ring.template pass<false>(a.A, p_new, red_sh, [&](int r, double sum) { a.q[r] = sum; acc[0] += p_new[r] * sum; },
-                                [&] { if (push) { PROF_T(c, 3); halo_wait(c, a); PROF_T(c, 13); } });
+                                [&](int) { if (push) { PROF_T(c, 3); halo_wait(c, a); PROF_T(c, 13); } });
+#endif
       ring.prefetch(a.A);
       PROF_T(c, 3);
       grid_allreduce<1, false>(c, a, acc, 0.0);
@@ -565,6 +606,7 @@ int pcg_persist_launch(const psp_mat *M, int n, const double *b, double *x, doub
   a.A.ind = M->d_ind; a.A.col = M->d_col; a.A.val = M->d_val; a.A.nb = M->nb;
   a.A.blk = reinterpret_cast<const int4 *>(M->d_blk);
   a.A.nint = M->nint;
+  a.A.blk_halo = reinterpret_cast<const int2 *>(M->d_blk_halo);
   a.n = n; a.b = b; a.x = x; a.r = r; a.p = p; a.p2 = p2; a.q = q; a.dinv = dinv;
   a.S = c.state; a.partials = g_partials2; a.sync = g_sync; a.dd = dm ? dist().dev : nullptr; a.l2_stream = l2_stream_for(n); a.dist_debug = (int)c.dist_debug;
   a.halo_owner = dm ? dm->d_owner : nullptr; a.halo_ridx = dm ? dm->d_ridx : nullptr;

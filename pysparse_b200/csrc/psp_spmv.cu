@@ -31,6 +31,7 @@
 // ll_mat.to_csr() order (lower row | diag | upper = transposed lower, rows
 // ascending), which is exactly the order in which sss_matvec accumulates
 // y[i]; the lower triangle + diagonal are kept as well for the SSOR sweeps.
+#include <climits>
 #include "psp_mat.cuh"
 #include "psp_epilogue.cuh"
 #include "psp_tma_ring.cuh"
@@ -186,7 +187,7 @@ __global__ void __launch_bounds__(kThreads) k_spmv_tma(SpmvArgs a) {
     if (V->done || (a.gate == 1 && V->cyc_done)) return;
   }
   MatView A;
-  A.ind = a.ind; A.col = a.col; A.val = a.val; A.nb = a.nb; A.nint = a.nb;
+  A.ind = a.ind; A.col = a.col; A.val = a.val; A.nb = a.nb; A.nint = a.nb; A.blk_halo = nullptr;
   A.blk = reinterpret_cast<const int4 *>(a.blk);
   Ring<STAGES> ring;
   ring.init(smem, full, a.l2_stream != 0);
@@ -314,6 +315,19 @@ static int finish_csr_upload(psp_mat *A, const std::vector<int> &ind, const int 
   PSP_TRY(upload(col, sizeof(int) * (size_t)A->fnnz, (void **)&A->d_col));
   PSP_TRY(upload(val, sizeof(double) * (size_t)A->fnnz, (void **)&A->d_val));
   PSP_TRY(upload(blk.data(), sizeof(int) * blk.size(), (void **)&A->d_blk));
+  if (own_cols >= 0) {
+    // per block (schedule order): the range of halo positions its entries read -- lets a
+    // persistent kernel unpack exactly what a boundary block needs right before it
+    std::vector<int> bh(2 * (size_t)A->nb, 0);
+    for (int i = A->nint; i < A->nb; i++) {
+      const int b = order[i];
+      int lo = INT_MAX, hi = -1;
+      for (int k = ind[rows[b]]; k < ind[rows[b + 1]]; k++)
+        if (col[k] >= own_cols) { lo = col[k] < lo ? col[k] : lo; hi = col[k] > hi ? col[k] : hi; }
+      bh[2 * (size_t)i] = lo - own_cols; bh[2 * (size_t)i + 1] = hi + 1 - own_cols;
+    }
+    PSP_TRY(upload(bh.data(), sizeof(int) * bh.size(), (void **)&A->d_blk_halo));
+  }
   PSP_CUDA(cudaStreamSynchronize(ctx().stream));   // host staging vectors die with this frame
   return PSP_OK;
 }
@@ -503,7 +517,7 @@ extern "C" int psp_sss_create(int n, int nnz, const int *ind, const int *col, co
 extern "C" void psp_mat_destroy(psp_mat *A) {
   if (!A) return;
   if (A->transp) psp_mat_destroy(A->transp);
-  cudaFree(A->d_ind); cudaFree(A->d_col); cudaFree(A->d_val); cudaFree(A->d_blk);
+  cudaFree(A->d_ind); cudaFree(A->d_col); cudaFree(A->d_val); cudaFree(A->d_blk); cudaFree(A->d_blk_halo);
   cudaFree(A->d_lind); cudaFree(A->d_lcol); cudaFree(A->d_lval); cudaFree(A->d_diag);
   cudaFree(A->d_x); cudaFree(A->d_y);
   delete A;

@@ -64,6 +64,7 @@ struct MatView {                          // device view of a CSR matrix + its r
   const double *val;
   int nb;
   int nint;                               // blocks [nint, nb) read halo columns (sharded matrices; else nb)
+  const int2 *blk_halo;                   // per block: [first, end) halo positions its entries read (or nullptr)
 };
 
 template <int STAGES>
@@ -144,21 +145,22 @@ struct Ring {
   // between grid barriers, use ordinary loads.
   //
   // The schedule lists the blocks that touch no halo column first (MatView::nint of
-  // them); haloop() is called once, by all threads, before this CTA's first block that
-  // does -- the sharded persistent kernels wait there for the neighbours' boundary
-  // values, which have been travelling while the interior blocks were multiplied.
+  // them); haloop(b) is called by all threads before this CTA's first block that does
+  // (PER_BLOCK: before every such block) -- the sharded persistent kernels wait there for
+  // the neighbours' boundary values, which have been travelling while the interior blocks
+  // were multiplied.
   template <bool NC, class RowOp>
   __device__ __forceinline__ void pass(const MatView &A, const double *x, double *red_sh, RowOp rowop) {
-    pass<NC>(A, x, red_sh, rowop, [] {});
+    pass<NC>(A, x, red_sh, rowop, [](int) {});
   }
-  template <bool NC, class RowOp, class HaloOp>
+  template <bool NC, bool PER_BLOCK = false, class RowOp, class HaloOp>
   __device__ __forceinline__ void pass(const MatView &A, const double *x, double *red_sh, RowOp rowop, HaloOp haloop) {
     const int tid = threadIdx.x;
     if (!prefetched) prefetch(A);
     prefetched = 0;
     bool halo_ready = false;
     for (int b = blockIdx.x; b < A.nb; b += gridDim.x) {
-      if (!halo_ready && b >= A.nint) { haloop(); halo_ready = true; }
+      if (b >= A.nint && (PER_BLOCK || !halo_ready)) { haloop(b); halo_ready = true; }
       const int stage = cursor;
       cursor = (cursor + 1) % STAGES;
       const int4 d = __ldg(A.blk + b);

@@ -26,6 +26,9 @@ ok = True
 cases = [("poisson3d", 24, "pcg", "ones", True), ("poisson3d", 48, "pcg", "ones", True),
          ("convdiff3d", 32, "bicgstab", "randn", True), ("convdiff3d", 32, "gmres", "randn", True),
          ("convdiff3d", 40, "gmres", "ones", False), ("convdiff3d", 24, "bicgstab", "randn", False)]
+only = os.environ.get("DIST_CASES")               # e.g. DIST_CASES=pcg: a quick subset
+if only:
+    cases = [c for c in cases if c[2] in only.split(",")]
 for kind, n, solver, rhs, jac in cases:
     N = n ** 3
     tol = 1e-10 if kind == "poisson3d" else 1e-8
