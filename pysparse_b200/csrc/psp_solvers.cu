@@ -17,7 +17,10 @@ namespace psp {
 
 int prec_apply_dev(psp_prec *K, const double *dx, double *dy, State *gateS);   // psp_precon.cu
 int pcg_persist_launch(const psp_mat *M, int n, const double *b, double *x, double *r, double *p, double *p2, double *q,
-                       const double *dinv, DistMat *dm);                        // psp_persist.cu
+                       const double *dinv, DistMat *dm);
+int bicg_persist_launch(const psp_mat *M, int n, const double *b, double *x, double *r, double *rhat, double *p,
+                        double *p2, double *phat, double *v, double *s, double *shat, double *t, const double *dinv,
+                        DistMat *dm);                        // psp_persist.cu
 
 // ------------------------------------------------------------------ generic functors
 struct FNormSq {            // red0 = sum a_i^2
@@ -506,6 +509,15 @@ static int solve_bicgstab(Solve &s, const double *b, double *x, double *work) {
   const bool ident = s.fusedK && !s.dinv;
   double *phat = ident ? p : phatb, *shat = ident ? sv : shatb;
   const int pub = s.dm ? kPublish : 0;     // multi-GPU: phat / shat are read by the neighbours
+  {
+    // single-launch path (psp_persist_bicg.cu): opt-in until it has been validated on a GPU
+    Ctx &c = ctx();
+    const psp_mat *M = s.dm ? s.dm->local : s.A.mat;
+    if (M && s.fusedK && c.bicg_persist == 1) {
+      double *p2 = (s.dm && dist().nslots >= 9) ? work + 8 * vs : nullptr;   // second p buffer (push model)
+      return bicg_persist_launch(M, (int)n, b, x, r, rhat, p, p2, phat, v, sv, shat, t, s.dinv, s.dm);
+    }
+  }
   PSP_TRY(launch_map(FNormSq{b}, n, EPI_BICG_NORMB));
   if (s.dm) {
     PSP_TRY(launch_map(FCopy{x, t}, n, EPI_NONE, pub));
