@@ -58,7 +58,11 @@ struct DistMail {                       // one all-reduce contribution
   // flag-in-data copy used by the persistent kernels: word 2k / 2k+1 = low / high half of
   // value k in the low 32 bits, the low 32 bits of the sequence number in the high ones --
   // every 8-byte word validates itself, so no release fence and a single NVLink trip
+#ifdef PSP_LL_ALLREDUCE
+  unsigned long long ll[2 * (kRedSlots + 1)];   // A/B build: the per-phase kernels use the words too
+#else
   unsigned long long ll[8];
+#endif
 };
 
 struct DistCtl {                        // lives in each rank's IPC-shared control block
@@ -249,6 +253,44 @@ __device__ __forceinline__ void dist_allreduce(DistDev *dd, double *totals, doub
   const unsigned long long seq = dd->red_seq + 1;
   const int slot = (int)(seq % kMailRing);
   __syncthreads();
+#ifdef PSP_LL_ALLREDUCE
+  // A/B build (-DPSP_LL_ALLREDUCE, prepared for round 2, not yet run): the flag-in-data words of
+  // the persistent kernels for the per-phase kernels too -- no st.release.sys (MEMBAR.SYS) per
+  // reduction.  Thread (w, j) sends word j of this rank's totals to rank w and fetches rank w's.
+  {
+    constexpr int NV = NS + (HASMAX ? 1 : 0);
+    __shared__ unsigned lbox[kMaxRanks][2 * (kRedSlots + 1)];
+    const unsigned tag = (unsigned)seq;
+    if ((int)threadIdx.x < W * 2 * NV) {
+      const int w = threadIdx.x / (2 * NV), j = threadIdx.x % (2 * NV), k = j >> 1;
+      const unsigned long long bits = (unsigned long long)__double_as_longlong(k < NS ? totals[k] : *totmax);
+      const unsigned half = (j & 1) ? (unsigned)(bits >> 32) : (unsigned)bits;
+      asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(&dd->ctl[w]->mail[slot][me].ll[j]),
+                   "l"(((unsigned long long)tag << 32) | half) : "memory");
+      const unsigned long long *src = &dd->ctl[me]->mail[slot][w].ll[j];
+      unsigned long long got;
+      do {
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(src) : "memory");
+      } while ((unsigned)(got >> 32) != tag);
+      lbox[w][j] = (unsigned)got;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int k = 0; k < NV; k++) {
+        double a = 0.0;
+        for (int w = 0; w < W; w++) {
+          const double v = __longlong_as_double((long long)(((unsigned long long)lbox[w][2 * k + 1] << 32) | lbox[w][2 * k]));
+          a = (k < NS) ? a + v : fmax(a, v);
+        }
+        if (k < NS) totals[k] = a; else *totmax = a;
+      }
+      dd->red_seq = seq;
+    }
+    (void)sh; (void)box;
+    return;
+  }
+#endif
   if ((int)threadIdx.x < W) {
     const int w = threadIdx.x;
     DistMail *dst = &dd->ctl[w]->mail[slot][me];
