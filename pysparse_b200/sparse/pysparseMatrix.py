@@ -1,14 +1,17 @@
-"""Higher-level sparse matrix classes over ``ll_mat`` (Python 3).
+"""Operator-style matrix classes on top of ``ll_mat`` (Python 3).
 
-Drop-in for ``pysparse.sparse.pysparseMatrix`` (reference:
-``pysparse/sparse/pysparseMatrix.py`` and ``sparseMatrix.py``; documented in
-``doc/pysparse/source/pysparsematrix.rst``): ``PysparseMatrix`` wraps an ``ll_mat`` and adds
-the arithmetic operators (``A + B``, ``A - B``, ``A * x``, ``x * A``, ``A * B``, ``2 * A``),
-``PysparseIdentityMatrix`` and ``PysparseSpDiagsMatrix`` build common matrices.
+Provides what ``pysparse.sparse.pysparseMatrix`` provides in the reference
+(``pysparse/sparse/pysparseMatrix.py``, ``sparseMatrix.py``; documented in
+``doc/pysparse/source/pysparsematrix.rst``): ``PysparseMatrix`` owns an ``ll_mat`` and lets it
+take part in expressions -- ``A + B``, ``A - B``, ``A * x``, ``x * A``, ``A * B``, ``2 * A``,
+``-A`` -- plus the bulk accessors ``put / take / addAt / find`` and their diagonal variants;
+``PysparseIdentityMatrix`` and ``PysparseSpDiagsMatrix`` are ready-made constructors.  The
+reference's worked examples for these classes are kept as tests
+(``tests/test_host_pysparse_matrix.py``).
 
-The wrapped ``ll_mat`` keeps a device copy that is rebuilt only when the matrix has been
-modified, so ``A * x`` in a loop uploads the matrix once and each product moves only the two
-vectors (the products themselves run on the GPU; there is no CPU path).
+Matrix-vector products run on the GPU.  The wrapped ``ll_mat`` keeps a device copy keyed on a
+modification counter, so a loop of ``A * x`` uploads the matrix once and each product moves
+only the two vectors.  There is no CPU path.
 """
 import numpy
 
@@ -18,48 +21,44 @@ __docformat__ = "restructuredtext"
 __all__ = ["SparseMatrix", "PysparseMatrix", "PysparseIdentityMatrix", "PysparseSpDiagsMatrix",
            "PysparseMatrix4Scipy"]
 
+_CELL = 11          # width of one printed cell
 
-def _is_scalar(x):
+
+def _is_number(x):
     return isinstance(x, (int, float, numpy.integer, numpy.floating)) and not isinstance(x, bool)
 
 
-class SparseMatrix:
-    """Abstract base: printing and the operator identities shared by all matrix classes
-    (reference ``sparseMatrix.py:49-140``)."""
+def _cell(v):
+    """One cell of the printed matrix: '---' for a zero, fixed point while the magnitude is
+    within e^-4 .. e^4, two-digit scientific notation beyond."""
+    if v == 0:
+        return "---".center(_CELL)
+    text = "%9.6f" % v if abs(numpy.log(abs(v))) <= 4 else "%9.2e" % v
+    return text.ljust(_CELL)
 
-    __array_priority__ = 100.0          # numpy defers ``ndarray * A`` to ``A.__rmul__``
-    __array_ufunc__ = None
+
+class SparseMatrix:
+    """Common behaviour of the matrix classes: text rendering and the operator identities
+    that follow from ``__add__`` / ``__sub__`` / ``__mul__``."""
+
+    __array_priority__ = 100.0
+    __array_ufunc__ = None          # ``ndarray * A`` is handed to ``A.__rmul__`` as a whole
 
     def getShape(self):
-        raise NotImplementedError
+        raise NotImplementedError("abstract class")
 
     def __str__(self):
-        # the reference's cell format (sparseMatrix.py:75-95): 11-wide cells, '---' for zeros,
-        # %9.6f while |ln|v|| <= 4, %9.2e beyond
-        width = 11
         nrow, ncol = self.getShape()
-        out = []
-        for i in range(nrow):
-            row = ""
-            for j in range(ncol):
-                v = self[i, j]
-                if v == 0:
-                    row += "---".center(width)
-                elif abs(numpy.log(abs(v))) <= 4:
-                    row += ("%9.6f" % v).ljust(width)
-                else:
-                    row += ("%9.2e" % v).ljust(width)
-            out.append(row)
-        return "\n".join(out)
+        return "\n".join("".join(_cell(self[i, j]) for j in range(ncol)) for i in range(nrow))
 
     def __repr__(self):
         return str(self.getMatrix())
 
     def __radd__(self, other):
-        return self.__add__(other)
+        return self + other
 
     def __rsub__(self, other):
-        return -(self.__sub__(other))
+        return -(self - other)
 
     def __neg__(self):
         return self * -1
@@ -69,386 +68,251 @@ class SparseMatrix:
 
 
 class PysparseMatrix(SparseMatrix):
-    """
-    A class wrapper for the ``ll_mat`` sparse matrix type that makes populating matrices
-    and operating on matrices and vectors read naturally.
+    """A sparse matrix that can be populated conveniently and used in expressions.
 
-    :keywords:
-        :nrow:       The number of rows of the matrix
-        :ncol:       The number of columns of the matrix
-        :size:       The common number of rows and columns, for a square matrix
-        :bandwidth:  The bandwidth (if creating a band matrix)
-        :matrix:     The starting ``ll_mat`` if there is one
-        :sizeHint:   A guess on the number of nonzero elements of the matrix
-        :symmetric:  A boolean indicating whether the matrix is symmetric.
-        :storeZeros: A boolean indicating whether to store zero values.
+    Keyword arguments (all optional):
+
+    ``nrow``, ``ncol``  shape of a new, empty matrix;  ``size``  shorthand for a square one;
+    ``symmetric``       store only the lower triangle (square matrices);
+    ``bandwidth``       expected bandwidth, ``sizeHint``  expected number of entries (only
+                        used to pre-size the container);
+    ``storeZeros``      keep explicitly assigned zeros;
+    ``matrix``          wrap this existing ``ll_mat`` instead of creating one.
     """
 
-    def __init__(self, **kwargs):
-        nrow = kwargs.get("nrow", 0)
-        ncol = kwargs.get("ncol", 0)
-        bandwidth = kwargs.get("bandwidth", 0)
-        matrix = kwargs.get("matrix", None)
-        sizeHint = kwargs.get("sizeHint", 0)
-        storeZeros = bool(kwargs.get("storeZeros", False))
-        symmetric = bool(kwargs.get("symmetric", False))
-        size = kwargs.get("size", 0)
-
-        if size > 0:
-            if nrow > 0 or ncol > 0:
-                if size != nrow or size != ncol:
-                    raise ValueError("size argument was given but does not match nrow and ncol")
-            else:
-                nrow = ncol = size
-
+    def __init__(self, *, nrow=0, ncol=0, size=0, bandwidth=0, matrix=None, sizeHint=0,
+                 symmetric=False, storeZeros=False):
         if matrix is not None:
             self.matrix = matrix
             return
-        if symmetric and nrow == ncol:
-            if not sizeHint:
-                sizeHint = nrow
-                if bandwidth > 0:
-                    sizeHint += 2 * (bandwidth - 1) * (2 * nrow - bandwidth - 2)
-            self.matrix = spmatrix.ll_mat_sym(nrow, max(int(sizeHint), 1), int(storeZeros))
+        if size > 0:
+            if (nrow > 0 or ncol > 0) and not (nrow == size and ncol == size):
+                raise ValueError("size argument was given but does not match nrow and ncol")
+            nrow = ncol = size
+        symmetric = bool(symmetric) and nrow == ncol
+        hint = int(sizeHint or 0)
+        if hint <= 0:                              # a rough count from the band structure
+            hint = nrow if symmetric else min(nrow, ncol)
+            if bandwidth > 0:
+                hint = bandwidth * max(hint, 1)
+        hint = max(hint, 1)
+        if symmetric:
+            self.matrix = spmatrix.ll_mat_sym(nrow, hint, int(bool(storeZeros)))
         else:
-            if not sizeHint:
-                sizeHint = min(nrow, ncol)
-                if bandwidth > 0:
-                    sizeHint = bandwidth * (2 * sizeHint - bandwidth - 1) // 2
-            self.matrix = spmatrix.ll_mat(nrow, ncol, max(int(sizeHint), 1), int(storeZeros))
+            self.matrix = spmatrix.ll_mat(nrow, ncol, hint, int(bool(storeZeros)))
 
-    # ---- queries ---------------------------------------------------------------------
+    # ---- queries
     def isSymmetric(self):
-        "Returns `True` is `self` is a symmetric matrix or `False` otherwise"
+        "``True`` when only the lower triangle is stored."
         return bool(self.matrix.issym)
 
-    def getNnz(self):
-        "Returns the number of nonzero elements of `self`"
-        return self.matrix.nnz
-
     def getMatrix(self):
-        "Returns the underlying `ll_mat` sparse matrix of `self`"
+        "The wrapped ``ll_mat``."
         return self.matrix
 
     def getShape(self):
-        "Returns the shape ``(nrow,ncol)`` of a sparse matrix"
+        "``(nrow, ncol)``."
         return self.matrix.shape
 
-    nnz = property(getNnz)
+    def getNnz(self):
+        "Number of stored entries."
+        return self.matrix.nnz
+
     shape = property(getShape)
+    nnz = property(getNnz)
 
     def copy(self):
-        "Returns a (deep) copy of a sparse matrix"
+        "A deep copy."
         return PysparseMatrix(matrix=self.matrix.copy())
 
-    # ---- element access (fancy indexing carries over from ll_mat) ---------------------
+    # ---- indexing: everything ``ll_mat`` accepts (integers, slices, lists, index arrays)
     def __getitem__(self, index):
-        m = self.matrix[index]
-        if isinstance(m, (int, float)):
-            return m
-        return PysparseMatrix(matrix=m)
+        item = self.matrix[index]
+        return item if isinstance(item, (int, float)) else PysparseMatrix(matrix=item)
 
     def __setitem__(self, index, value):
-        self.matrix[index] = value.matrix if isinstance(value, PysparseMatrix) else value
+        self.matrix[index] = value.getMatrix() if isinstance(value, PysparseMatrix) else value
 
-    # ---- addition / subtraction --------------------------------------------------------
-    def _iadd(self, other, sign=1):
-        if self.isSymmetric() and not other.isSymmetric():
-            self.matrix.generalize()
-        self.matrix.shift(sign, other.getMatrix())
-        return self
-
-    def __iadd__(self, other):
-        return self._iadd(other)
-
-    def __isub__(self, other):
-        return self._iadd(other, sign=-1)
+    # ---- sums
+    def _shifted(self, sign, other, inplace):
+        if self.getShape() != other.getShape():
+            raise TypeError("Only sparse matrices of the same size may be %s" % ("added" if sign > 0 else "subtracted"))
+        target = self.matrix if inplace else self.matrix.copy()
+        if target.issym and not other.isSymmetric():
+            target.generalize()                    # symmetric (+/-) general needs general storage
+        target.shift(sign, other.getMatrix())
+        return self if inplace else PysparseMatrix(matrix=target)
 
     def __add__(self, other):
-        """
-        Add two sparse matrices (a new matrix is returned), or add a number to every STORED
-        entry of a matrix.
-
-            >>> L = PysparseMatrix(size = 3)
-            >>> L.put([3.,10.,numpy.pi,2.5], [0,0,1,2], [2,1,1,0])
-            >>> print(L + PysparseIdentityMatrix(size = 3))
-             1.000000  10.000000   3.000000
-                ---     4.141593      ---
-             2.500000      ---     1.000000
-            >>> print(L + 3)
-                ---    13.000000   6.000000
-                ---     6.141593      ---
-             5.500000      ---        ---
-        """
-        if _is_scalar(other):
+        """``A + B`` for two matrices of equal shape; ``A + c`` adds the number ``c`` to every
+        STORED entry (``A + 0`` is ``A`` itself)."""
+        if _is_number(other):
             if other == 0:
                 return self
-            L = self.copy()
-            val, irow, jcol = L.find()
-            L.matrix.update_add_at(other * numpy.ones(val.shape), irow, jcol)
-            return L
+            result = self.copy()
+            val, irow, jcol = result.find()
+            result.matrix.update_add_at(numpy.full(len(val), float(other)), irow, jcol)
+            return result
         if isinstance(other, PysparseMatrix):
-            if self.getShape() != other.getShape():
-                raise TypeError("Only sparse matrices of the same size may be added")
-            L = self.matrix.copy()
-            if self.isSymmetric() and not other.isSymmetric():
-                L.generalize()
-            L.shift(1, other.getMatrix())
-            return PysparseMatrix(matrix=L)
+            return self._shifted(+1, other, inplace=False)
         return NotImplemented
 
     def __sub__(self, other):
-        if _is_scalar(other):
-            return self.__add__(-other)
+        if _is_number(other):
+            return self + (-other)
         if isinstance(other, PysparseMatrix):
-            if self.getShape() != other.getShape():
-                raise TypeError("Only sparse matrices of the same size may be subtracted")
-            L = self.matrix.copy()
-            if self.isSymmetric() and not other.isSymmetric():
-                L.generalize()
-            L.shift(-1, other.getMatrix())
-            return PysparseMatrix(matrix=L)
+            return self._shifted(-1, other, inplace=False)
         return NotImplemented
 
-    # ---- products ------------------------------------------------------------------------
-    def __mul__(self, other):
-        """
-        Multiply a sparse matrix by another sparse matrix, by a vector (the matrix-vector
-        product runs on the GPU) or by a scalar.
+    def __iadd__(self, other):
+        return self._shifted(+1, other, inplace=True)
 
-            >>> L1 = PysparseMatrix(size = 3)
-            >>> L1.put([3.,10.,numpy.pi,2.5], [0,0,1,2], [2,1,1,0])
-            >>> L2 = PysparseMatrix(size = 3)
-            >>> L2.put(numpy.ones(3), numpy.arange(3), numpy.arange(3))
-            >>> L2.put([4.38,12357.2,1.1], [2,1,0], [1,0,2])
-            >>> tmp = numpy.array(((1.23572000e+05, 2.31400000e+01, 3.00000000e+00),
-            ...                    (3.88212887e+04, 3.14159265e+00, 0.00000000e+00),
-            ...                    (2.50000000e+00, 0.00000000e+00, 2.75000000e+00)))
-            >>> bool(numpy.allclose((L1 * L2).getNumpyArray(), tmp))
-            True
-        """
-        M, N = self.getShape()
+    def __isub__(self, other):
+        return self._shifted(-1, other, inplace=True)
+
+    # ---- products
+    def __mul__(self, other):
+        """``A * B`` (sparse product, a new matrix), ``A * x`` for a vector of length ``ncol``
+        (a new NumPy array, computed on the GPU) or ``A * c`` for a number."""
+        nrow, ncol = self.getShape()
         if isinstance(other, PysparseMatrix):
-            if N != other.getShape()[0]:
+            if other.getShape()[0] != ncol:
                 raise TypeError("Matrices dimensions do not match for product")
             return PysparseMatrix(matrix=spmatrix.matrixmultiply(self.matrix, other.getMatrix()))
         shape = numpy.shape(other)
         if shape == ():
-            p = self.matrix.copy()
-            p.scale(float(other))
-            return PysparseMatrix(matrix=p)
-        if shape == (N,):
-            x = numpy.ascontiguousarray(other, dtype=numpy.float64)
-            y = numpy.empty(M)
-            self.matrix.matvec(x, y)
+            scaled = self.matrix.copy()
+            scaled.scale(float(other))
+            return PysparseMatrix(matrix=scaled)
+        if shape == (ncol,):
+            y = numpy.empty(nrow)
+            self.matrix.matvec(numpy.ascontiguousarray(other, dtype=numpy.float64), y)
             return y
         raise TypeError("Cannot multiply objects")
 
-    def __imul__(self, other):
-        if not _is_scalar(other):
-            raise TypeError("In-place multiplication is with scalars only")
-        self.matrix.scale(float(other))
-        return self
-
     def __rmul__(self, other):
-        # other * A  is really  A^T * other  for a vector
+        "``x * A`` for a vector of length ``nrow`` is ``A^T x``; ``c * A`` scales."
         if isinstance(other, numpy.ndarray) and other.ndim == 1:
-            M, N = self.getShape()
-            if other.shape != (M,):
+            nrow, ncol = self.getShape()
+            if other.shape != (nrow,):
                 raise TypeError("Cannot multiply objects")
-            y = numpy.empty(N)
+            y = numpy.empty(ncol)
             self.matrix.matvec_transp(numpy.ascontiguousarray(other, dtype=numpy.float64), y)
             return y
         return self * other
 
+    def __imul__(self, other):
+        if not _is_number(other):
+            raise TypeError("In-place multiplication is with scalars only")
+        self.matrix.scale(float(other))
+        return self
+
     def matvec(self, x):
-        "``A.matvec(x)`` returns ``A * x`` (the one-argument form SciPy's solvers call)."
+        "``A * x`` (the one-argument form SciPy-style solvers call)."
         return self * x
 
-    # ---- scaling ----------------------------------------------------------------------
     def col_scale(self, v):
-        "In-place column scaling: ``A[:,i] *= v[i]``."
+        "``A[:, j] *= v[j]`` in place."
         return self.matrix.col_scale(v)
 
     def row_scale(self, v):
-        "In-place row scaling: ``A[i,:] *= v[i]``."
+        "``A[i, :] *= v[i]`` in place."
         return self.matrix.row_scale(v)
 
-    # ---- bulk element access ------------------------------------------------------------
+    # ---- bulk access
     def find(self):
-        """
-        The matrix in coordinate (triplet) format, three NumPy arrays:
-
-            >>> L = PysparseMatrix(size = 3)
-            >>> L.put([3.,10.,numpy.pi,2.5], [0,0,1,2], [2,1,1,0])
-            >>> (val,irow,jcol) = L.find()
-            >>> irow.tolist(), jcol.tolist()
-            ([0, 0, 1, 2], [1, 2, 1, 0])
-        """
+        "``(val, irow, jcol)``: the stored entries in coordinate format, row by row."
         return self.matrix.find()
 
-    def _default_ids(self, value, id1, id2):
-        nrow, ncol = self.getShape()
-        if id2 is None and id1 is not None:
-            id2 = id1
-        scalar = _is_scalar(value)
-        if id1 is None:
-            id1 = numpy.arange(nrow if scalar else len(value), dtype=numpy.int64)
-        if id2 is None:
-            id2 = numpy.arange(ncol if scalar else len(value), dtype=numpy.int64)
-        return id1, id2
-
     def put(self, value, id1=None, id2=None):
-        """
-        Put elements of ``value`` at positions of the matrix corresponding to ``(id1, id2)``
-
-            >>> L = PysparseMatrix(size = 3)
-            >>> L.put( [3.,10.,numpy.pi,2.5], [0,0,1,2], [2,1,1,0] )
-            >>> print(L)
-                ---    10.000000   3.000000
-                ---     3.141593      ---
-             2.500000      ---        ---
-            >>> L.put(2*numpy.pi, range(3), range(3))
-            >>> print(L)
-             6.283185  10.000000   3.000000
-                ---     6.283185      ---
-             2.500000      ---     6.283185
-
-        If ``value`` is a scalar, it acts as the constant vector of appropriate length.  If
-        ``id1`` is omitted it is replaced with ``range(nrow)``; if ``id2`` is omitted it is
-        ``id1`` when that is present, ``range(ncol)`` otherwise.
-        """
-        id1, id2 = self._default_ids(value, id1, id2)
-        self.matrix.put(value, list(id1) if isinstance(id1, range) else id1,
-                        list(id2) if isinstance(id2, range) else id2)
+        """``A[id1[k], id2[k]] = value[k]``.  A scalar ``value`` stands for a constant vector.
+        Missing ``id2`` means ``id1``; missing both means the leading diagonal positions
+        (``range(len(value))``, or the whole diagonal for a scalar)."""
+        nrow, ncol = self.getShape()
+        if id1 is not None and id2 is None:
+            id2 = id1
+        count = None if _is_number(value) else len(value)
+        if id1 is None:
+            id1 = numpy.arange(nrow if count is None else count, dtype=numpy.int64)
+        if id2 is None:
+            id2 = numpy.arange(ncol if count is None else count, dtype=numpy.int64)
+        self.matrix.put(value, numpy.asarray(id1, dtype=numpy.int64), numpy.asarray(id2, dtype=numpy.int64))
 
     def putDiagonal(self, vector):
-        """
-        Put elements of ``vector`` along diagonal of matrix
-
-            >>> L = PysparseMatrix(size = 3)
-            >>> L.putDiagonal([3.,10.,numpy.pi])
-            >>> L.putDiagonal([10.,3.])
-            >>> print(L)
-            10.000000      ---        ---
-                ---     3.000000      ---
-                ---        ---     3.141593
-        """
-        if _is_scalar(vector):
+        "Assign the leading ``len(vector)`` diagonal entries (all of them for a scalar)."
+        if _is_number(vector):
             ids = numpy.arange(self.getShape()[0])
             self.put(vector, ids, ids)
         else:
             self.matrix.put(vector)
 
     def take(self, id1=None, id2=None):
-        "``val[i] = A[id1[i], id2[i]]`` as a new NumPy array (the diagonal if no indices are given)."
-        nrow, ncol = self.getShape()
-        if id2 is None and id1 is not None:
-            id2 = id1
+        "A new array with ``A[id1[k], id2[k]]`` (the diagonal when no indices are given)."
         if id1 is None:
-            id1 = numpy.arange(min(nrow, ncol), dtype=numpy.int64)
+            id1 = numpy.arange(min(self.getShape()), dtype=numpy.int64)
         if id2 is None:
             id2 = id1
-        vector = numpy.zeros(len(id1), "d")
-        self.matrix.take(vector, numpy.asarray(id1), numpy.asarray(id2))
-        return vector
+        out = numpy.zeros(len(id1))
+        self.matrix.take(out, numpy.asarray(id1, dtype=numpy.int64), numpy.asarray(id2, dtype=numpy.int64))
+        return out
 
     def takeDiagonal(self):
-        "The diagonal of the matrix as a NumPy array."
-        ids = numpy.arange(min(self.getShape()))
-        return self.take(ids, ids)
+        "The diagonal as a NumPy array."
+        return self.take()
 
     def addAt(self, vector, id1, id2):
-        """
-        Add elements of ``vector`` to the positions in the matrix corresponding to ``(id1,id2)``
-
-            >>> L = PysparseMatrix(size = 3)
-            >>> L.put([3.,10.,numpy.pi,2.5], [0,0,1,2], [2,1,1,0])
-            >>> L.addAt((1.73,2.2,8.4,3.9,1.23), (1,2,0,0,1), (2,2,0,0,2))
-            >>> print(L)
-            12.300000  10.000000   3.000000
-                ---     3.141593   2.960000
-             2.500000      ---     2.200000
-        """
+        "``A[id1[k], id2[k]] += vector[k]``; repeated positions accumulate."
         self.matrix.update_add_at(vector, id1, id2)
 
     def addAtDiagonal(self, vector):
-        "Add the components of ``vector`` (or a scalar) to the diagonal elements of the matrix."
-        if _is_scalar(vector):
-            n = self.getShape()[0]
-            ids = numpy.arange(n)
-            self.addAt(numpy.full(n, float(vector)), ids, ids)
-        else:
-            ids = numpy.arange(len(vector))
-            self.addAt(vector, ids, ids)
+        "Add a vector (to the leading diagonal entries) or a number (to the whole diagonal)."
+        if _is_number(vector):
+            vector = numpy.full(self.getShape()[0], float(vector))
+        ids = numpy.arange(len(vector))
+        self.addAt(vector, ids, ids)
 
     def getNumpyArray(self):
-        "Convert a sparse matrix to a dense NumPy matrix."
-        shape = self.getShape()
-        indices = numpy.indices(shape)
-        return numpy.reshape(self.take(indices[0].ravel(), indices[1].ravel()), shape)
+        "A dense copy."
+        nrow, ncol = self.getShape()
+        rows, cols = numpy.indices((nrow, ncol))
+        return self.take(rows.ravel(), cols.ravel()).reshape(nrow, ncol)
 
     def exportMmf(self, filename):
-        "Exports the matrix to a Matrix Market file of the given filename."
+        "Write the matrix in MatrixMarket coordinate format."
         self.matrix.export_mtx(filename)
 
 
 class PysparseIdentityMatrix(PysparseMatrix):
-    """
-    A sparse identity matrix.
-
-        >>> print(PysparseIdentityMatrix(size = 3))
-         1.000000      ---        ---
-            ---     1.000000      ---
-            ---        ---     1.000000
-    """
+    "The ``size`` x ``size`` identity, stored symmetrically."
 
     def __init__(self, size):
-        PysparseMatrix.__init__(self, nrow=size, ncol=size, bandwidth=1, symmetric=True)
-        ids = numpy.arange(size)
-        self.put(numpy.ones(size), ids, ids)
+        super().__init__(size=size, bandwidth=1, symmetric=True)
+        self.putDiagonal(numpy.ones(size))
 
 
 class PysparseSpDiagsMatrix(PysparseMatrix):
-    """
-    A banded matrix with specified diagonals.
-
-    *Example:* a tridiagonal matrix with 1's on the diagonal, 2's above and -2's below it.
-
-        >>> from numpy import ones
-        >>> e = ones(5)
-        >>> print(PysparseSpDiagsMatrix(size=5, vals=(-2*e,e,2*e), pos=(-1,0,1)))
-         1.000000   2.000000      ---        ---        ---
-        -2.000000   1.000000   2.000000      ---        ---
-            ---    -2.000000   1.000000   2.000000      ---
-            ---        ---    -2.000000   1.000000   2.000000
-            ---        ---        ---    -2.000000   1.000000
-
-    Since the ``pos[k]``-th diagonal has ``size-|pos[k]|`` elements, only that many first
-    elements of ``vals[k]`` are inserted.  If the matrix is requested to be symmetric,
-    elements above the main diagonal are not inserted.
-    """
+    """A square banded matrix given by its diagonals: ``vals[k]`` goes on diagonal ``pos[k]``
+    (0 the main diagonal, positive above, negative below); diagonal ``d`` has ``size - |d|``
+    entries and takes that many leading elements of ``vals[k]``.  With ``symmetric=True`` the
+    diagonals above the main one are not stored."""
 
     def __init__(self, size, vals, pos, **kwargs):
-        pos = numpy.asarray(pos, dtype=numpy.int64)
-        bw = int(max(numpy.abs(pos))) if len(pos) else 0
-        diags = size - numpy.abs(pos)
+        pos = [int(d) for d in pos]
         kwargs.pop("bandwidth", None)
         kwargs.pop("sizeHint", None)
-        PysparseMatrix.__init__(self, nrow=size, ncol=size, bandwidth=bw, sizeHint=int(sum(diags)), **kwargs)
-        for k in range(len(pos)):
-            dk, d = int(diags[k]), int(pos[k])
-            v = numpy.asarray(vals[k], dtype=numpy.float64)[:dk]
-            if d > 0 and self.isSymmetric():
-                continue                       # above the diagonal of a symmetric matrix: not stored
-            if d >= 0:
-                self.put(v, numpy.arange(dk), d + numpy.arange(dk))
-            else:
-                self.put(v, -d + numpy.arange(dk), numpy.arange(dk))
+        super().__init__(size=size, bandwidth=max([abs(d) for d in pos] + [0]),
+                         sizeHint=sum(size - abs(d) for d in pos), **kwargs)
+        for d, v in zip(pos, vals):
+            length = size - abs(d)
+            if length <= 0 or (d > 0 and self.isSymmetric()):
+                continue
+            k = numpy.arange(length)
+            rows, cols = (k, k + d) if d >= 0 else (k - d, k)
+            self.put(numpy.asarray(v, dtype=numpy.float64)[:length], rows, cols)
 
 
 class PysparseMatrix4Scipy(PysparseMatrix):
-    "A ``PysparseMatrix`` whose ``matvec(x, y)`` has the two-argument ``ll_mat`` signature."
+    "A ``PysparseMatrix`` whose ``matvec(x, y)`` has the two-argument ``ll_mat`` form."
 
     def matvec(self, x, y):
         return self.matrix.matvec(x, y)

@@ -1,11 +1,9 @@
-"""``cputime()``: user CPU time of this process in seconds (reference: ``pysparse/tools/sptime.py``)."""
-try:
-    import resource
+"""Process CPU time for the timing loops of example scripts (``pysparse.tools.sptime``)."""
+import time
 
-    def cputime():
-        return resource.getrusage(resource.RUSAGE_SELF)[0]
-except ImportError:                                   # pragma: no cover
-    import time
+__all__ = ["cputime"]
 
-    def cputime():
-        return time.process_time()
+
+def cputime():
+    "Seconds of CPU time (user + system) this process has used so far."
+    return time.process_time()
