@@ -148,8 +148,13 @@ __device__ __forceinline__ void st_release_gpu_u64(unsigned long long *p, unsign
 // reads the partials and only one polls the mailboxes.  On return tot[0..NS) (and
 // tot[kRedSlots] for the max) are valid in every thread of every CTA, and all global
 // writes made before the call are visible grid-wide.
-template <int NS, bool HASMAX>
-__device__ __forceinline__ void grid_allreduce(PersistCtx &c, const PersistArgs &a, const double *acc, double mx) {
+//
+// last_op(tot) is run by thread 0 of the CTA with the last ticket after the totals (cross-GPU
+// included) are known and BEFORE the others are released: the place for scalar work that
+// must happen exactly once (solvers whose epilogue updates global arrays, e.g. GMRES).
+template <int NS, bool HASMAX, class LastOp>
+__device__ __forceinline__ void grid_allreduce_op(PersistCtx &c, const PersistArgs &a, const double *acc, double mx,
+                                                  LastOp last_op) {
   __shared__ int is_last;
   __shared__ unsigned box[kMaxRanks][8];
   const unsigned gen = ++c.gen;
@@ -224,6 +229,7 @@ __device__ __forceinline__ void grid_allreduce(PersistCtx &c, const PersistArgs 
       }
     }
     if (threadIdx.x == 0) {
+      last_op(c.tot);
 #pragma unroll
       for (int s = 0; s < NS; s++) res[s] = c.tot[s];
       if (HASMAX) res[kRedSlots] = c.tot[kRedSlots];
@@ -240,6 +246,11 @@ __device__ __forceinline__ void grid_allreduce(PersistCtx &c, const PersistArgs 
   }
   __syncthreads();
   PROF_T(c, 9);
+}
+
+template <int NS, bool HASMAX>
+__device__ __forceinline__ void grid_allreduce(PersistCtx &c, const PersistArgs &a, const double *acc, double mx) {
+  grid_allreduce_op<NS, HASMAX>(c, a, acc, mx, [](const double *) {});
 }
 
 // thread 0 of every CTA advances its copy of the state; all copies stay identical
@@ -322,11 +333,10 @@ __device__ __forceinline__ void halo_unpack(PersistCtx &c, const PersistArgs &a,
   }
 }
 
-#ifdef PSP_BLOCK_UNPACK
-// Variant (A/B build -DPSP_BLOCK_UNPACK, not the default): no unpack pass and no tickets.
-// A boundary block's CTA unpacks, right before the block, exactly the halo positions that
-// block reads (MatView::blk_halo); ranges of different blocks may overlap, the CTAs then
-// write identical values.  Takes the unpack off the start of the SpMV pass.
+// Block-local unpack (the PCG kernel uses it in the A/B build -DPSP_BLOCK_UNPACK only): no
+// unpack pass and no tickets.  A boundary block's CTA unpacks, right before the block, exactly
+// the halo positions that block reads (MatView::blk_halo); ranges of different blocks may
+// overlap, the CTAs then write identical values.
 __device__ __forceinline__ void halo_unpack_block(PersistCtx &c, const PersistArgs &a, double *vec, int b) {
   if (c.debug >= 1) return;
   DistDev *dd = c.dd;
@@ -343,7 +353,18 @@ __device__ __forceinline__ void halo_unpack_block(PersistCtx &c, const PersistAr
   }
   __syncthreads();
 }
-#endif
+
+// Late push: after the grid barrier that completes `vec`, every thread sends its share of the
+// boundary entries as they are (no recomputation, so no double buffering); to be paired with
+// halo_unpack_block.  Counts as one exchange.
+__device__ __forceinline__ void halo_push_late(PersistCtx &c, const PersistArgs &a, const double *vec) {
+  if (c.debug < 1) {
+    const unsigned stride = gridDim.x * blockDim.x;
+    for (unsigned s = blockIdx.x * blockDim.x + threadIdx.x; s < (unsigned)a.nsend; s += stride)
+      halo_send(c, a, s, vec[a.send_row[s]]);
+  }
+  c.pubs += 1;
+}
 
 // before the first row block that reads a halo column
 __device__ __forceinline__ void halo_wait(PersistCtx &c, const PersistArgs &a) {
