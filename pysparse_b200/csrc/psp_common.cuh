@@ -126,6 +126,7 @@ struct Ctx {
   long long pcg_persist = -1; // single-launch PCG: 1 always, 0 never, -1 automatic
   long long ssor_engine = 0;  // SSOR sweeps: 0 automatic, 1 grid-wide barrier, 2 cluster barrier
   long long ssor_cluster = 8; // CTAs in the sweep cluster (8 portable, 16 non-portable)
+  long long gmres_persist = 0; // 1: single-launch GMRES kernel (psp_persist_gmres.cu; not yet validated on a GPU)
   long long bicg_persist = 0; // 1: single-launch BiCGSTAB kernel (psp_persist_bicg.cu; not yet validated on a GPU)
   long long dist_push = 1;    // sharded single-launch PCG: push the halo to the neighbours (needs the send map)
   long long dist_debug = 0;   // timing diagnostics only (results invalid): 1 skip halo pull, 2 also skip the cross-GPU all-reduce

@@ -204,16 +204,18 @@ __device__ __forceinline__ void grid_allreduce_op(PersistCtx &c, const PersistAr
       const int W = dd->world, me = dd->rank;
       const int slot = (int)(seq % kMailRing);
       const unsigned tag = seq;
-      if ((int)threadIdx.x < W * 2 * NV) {
-        const int w = threadIdx.x / (2 * NV), j = threadIdx.x % (2 * NV);
-        const int k = j >> 1;
-        const unsigned long long bits = (unsigned long long)__double_as_longlong(k < NS ? c.tot[k] : c.tot[kRedSlots]);
-        const unsigned half = (j & 1) ? (unsigned)(bits >> 32) : (unsigned)bits;
-        st_relaxed_sys_u64(&dd->ctl[w]->mail[slot][me].ll[j], ((unsigned long long)tag << 32) | half);
-        const unsigned long long *src = &dd->ctl[me]->mail[slot][w].ll[j];
-        unsigned long long got;
-        do { got = ld_relaxed_sys_u64(src); } while ((unsigned)(got >> 32) != tag);
-        box[w][j] = (unsigned)got;
+      if constexpr (NV > 0) {                       // NV == 0: a pure barrier, nothing to exchange
+        if ((int)threadIdx.x < W * 2 * NV) {
+          const int w = threadIdx.x / (2 * NV), j = threadIdx.x % (2 * NV);
+          const int k = j >> 1;
+          const unsigned long long bits = (unsigned long long)__double_as_longlong(k < NS ? c.tot[k] : c.tot[kRedSlots]);
+          const unsigned half = (j & 1) ? (unsigned)(bits >> 32) : (unsigned)bits;
+          st_relaxed_sys_u64(&dd->ctl[w]->mail[slot][me].ll[j], ((unsigned long long)tag << 32) | half);
+          const unsigned long long *src = &dd->ctl[me]->mail[slot][w].ll[j];
+          unsigned long long got;
+          do { got = ld_relaxed_sys_u64(src); } while ((unsigned)(got >> 32) != tag);
+          box[w][j] = (unsigned)got;
+        }
       }
       __syncthreads();
       if (threadIdx.x == 0) {

@@ -243,6 +243,7 @@ extern "C" int psp_set_option(const char *name, long long value) {
   else if (!strcmp(name, "dist_debug")) c.dist_debug = value;
   else if (!strcmp(name, "dist_push")) c.dist_push = value;
   else if (!strcmp(name, "bicg_persist")) c.bicg_persist = value;
+  else if (!strcmp(name, "gmres_persist")) c.gmres_persist = value;
   else if (!strcmp(name, "ssor_cluster")) c.ssor_cluster = (value >= 1 && value <= 16) ? value : 8;
   else { set_error("unknown option '%s'", name); return PSP_ERR_ARG; }
   return PSP_OK;
@@ -263,5 +264,6 @@ extern "C" long long psp_get_option(const char *name) {
   if (!strcmp(name, "dist_debug")) return c.dist_debug;
   if (!strcmp(name, "dist_push")) return c.dist_push;
   if (!strcmp(name, "bicg_persist")) return c.bicg_persist;
+  if (!strcmp(name, "gmres_persist")) return c.gmres_persist;
   return -1;
 }

@@ -18,6 +18,8 @@ namespace psp {
 int prec_apply_dev(psp_prec *K, const double *dx, double *dy, State *gateS);   // psp_precon.cu
 int pcg_persist_launch(const psp_mat *M, int n, const double *b, double *x, double *r, double *p, double *p2, double *q,
                        const double *dinv, DistMat *dm);
+int gmres_persist_launch(const psp_mat *M, int n, const double *b, double *x, double *V, double *W, double *xs,
+                         size_t N, int m, const double *dinv, const double *g, DistMat *dm);
 int bicg_persist_launch(const psp_mat *M, int n, const double *b, double *x, double *r, double *rhat, double *p,
                         double *p2, double *phat, double *v, double *s, double *shat, double *t, const double *dinv,
                         DistMat *dm);                        // psp_persist.cu
@@ -740,6 +742,16 @@ static int solve_gmres(Solve &s, const double *b, double *x, int m) {
     }
     return PSP_OK;
   };
+  {
+    // single-launch path (psp_persist_gmres.cu): opt-in until it has been validated on a GPU
+    const psp_mat *M = s.dm ? s.dm->local : s.A.mat;
+    if (M && s.fusedK && c.gmres_persist == 1 && m <= 256) {
+      st = gmres_persist_launch(M, (int)n, b, x, V, W, s.dm ? xs : x, N, m, s.dinv, G.g, s.dm);
+      cudaStreamSynchronize(c.stream);
+      cleanup();
+      return st;
+    }
+  }
   st = run();
   cudaStreamSynchronize(c.stream);
   cleanup();
