@@ -315,10 +315,11 @@ static int finish_csr_upload(psp_mat *A, const std::vector<int> &ind, const int 
   PSP_TRY(upload(col, sizeof(int) * (size_t)A->fnnz, (void **)&A->d_col));
   PSP_TRY(upload(val, sizeof(double) * (size_t)A->fnnz, (void **)&A->d_val));
   PSP_TRY(upload(blk.data(), sizeof(int) * blk.size(), (void **)&A->d_blk));
+  std::vector<int> bh;                             // outlives the asynchronous copy below
   if (own_cols >= 0) {
     // per block (schedule order): the range of halo positions its entries read -- lets a
     // persistent kernel unpack exactly what a boundary block needs right before it
-    std::vector<int> bh(2 * (size_t)A->nb, 0);
+    bh.assign(2 * (size_t)A->nb, 0);
     for (int i = A->nint; i < A->nb; i++) {
       const int b = order[i];
       int lo = INT_MAX, hi = -1;
