@@ -229,3 +229,37 @@ extern "C" int flow_gmres(int n, const int *ind, const int *col, const double *v
   finish(S, info, iter, relres);
   return 0;
 }
+
+// ---------------------------------------------------------------- scalar state for Python-driven flows
+// (tests/test_persist_flow.py emulates the SHARDED kernels rank by rank in NumPy and needs the
+// product's scalar logic: one State shared by all emulated ranks, as on the GPUs where every
+// rank computes identical scalars)
+extern "C" void *st_new(double tol, int maxit, int mdim) { return new State(make_state(tol, maxit, mdim)); }
+extern "C" void st_free(void *s) { delete (State *)s; }
+extern "C" void st_epi(void *s, int epi, double r0, double r1, double mx) {
+  State *S = (State *)s;
+  S->red[0] = r0; S->red[1] = r1; S->redmax = mx;
+  run_epilogue(epi, S, nullptr);
+}
+extern "C" double st_v(void *s, int idx) { return ((State *)s)->v[idx]; }
+extern "C" double st_relres(void *s) { return ((State *)s)->relres; }
+extern "C" int st_int(void *s, int which) {
+  const State *S = (const State *)s;
+  switch (which) {
+    case 0: return S->done;
+    case 1: return S->info;
+    case 2: return S->iter;
+    case 3: return S->it;
+    case 4: return S->phase;
+    case 5: return S->stag;
+    default: return -1;
+  }
+}
+extern "C" int epi_id(const char *name) {
+#define PSP_EPI(x) if (!std::strcmp(name, #x)) return (int)x;
+  PSP_EPI(EPI_PCG_NORMB) PSP_EPI(EPI_PCG_RESID0_J) PSP_EPI(EPI_PCG_PQ) PSP_EPI(EPI_PCG_UPDATE_J)
+  PSP_EPI(EPI_BICG_NORMB) PSP_EPI(EPI_BICG_RES0) PSP_EPI(EPI_BICG_ALPHA) PSP_EPI(EPI_BICG_OMEGA) PSP_EPI(EPI_BICG_RES)
+  PSP_EPI(V_ALPHA) PSP_EPI(V_BETA) PSP_EPI(B_ALPHA) PSP_EPI(B_BETA) PSP_EPI(B_OMEGA)
+#undef PSP_EPI
+  return -1;
+}
