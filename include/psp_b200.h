@@ -110,6 +110,10 @@ int psp_jacobi_create(psp_mat *a, int n, const double *diag, double omega, int s
  * sweep); the sweeps keep the reference's lexicographic dependency order. */
 int psp_ssor_create(psp_mat *sss, double omega, int steps, psp_prec **out);
 
+/* (Re)bind the matrix a multi-step Jacobi preconditioner multiplies with (the host layer calls
+ * it before every use: the device copy of a mutable ll_mat may have been rebuilt). */
+int psp_prec_set_matrix(psp_prec *k, psp_mat *a);
+
 void psp_prec_destroy(psp_prec *k);
 
 /* y := K^-1 x with HOST vectors (contiguous): Jacobi_precon / SSOR_precon
@@ -237,8 +241,8 @@ int psp_dist_solve_dev(int solver, psp_dmat *A, psp_prec *K, const double *db, d
 
 /* ---- tuning knobs (default to reference semantics) --------------------- */
 /* name: "spmv_variant" (0 auto, 1 scalar-stream, 2 vector-stream ...),
- *       "poll_chunk" (iterations enqueued between convergence polls),
- *       "use_graph" (capture iteration bodies in CUDA graphs)              */
+ *       "poll_chunk" (iterations enqueued between convergence polls), ...
+ * the full list is in DESIGN.md section 1; unknown names return PSP_ERR_ARG    */
 int psp_set_option(const char *name, long long value);
 long long psp_get_option(const char *name);
 

@@ -119,6 +119,11 @@ struct Ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evpoll[2] = {nullptr, nullptr};
   double last_ms = 0.0;
   long long launches = 0;
+  int solve_depth = 0;              // > 0 while a solve is running (nested solves get their own frame)
+  // device scratch kept between calls (b, x and the work vectors of psp_solve): a solve of a
+  // small system costs a few kernel launches, three cudaMalloc/cudaFree pairs would dominate it
+  double *pool[3] = {nullptr, nullptr, nullptr};
+  size_t pool_cap[3] = {0, 0, 0};
   // options
   long long spmv_variant = 0;
   long long spmv_ctas = 0;    // cap on resident CTAs per SM for the TMA SpMV (0: occupancy limit)
@@ -131,7 +136,6 @@ struct Ctx {
   long long dist_push = 1;    // sharded single-launch PCG: push the halo to the neighbours (needs the send map)
   long long dist_debug = 0;   // timing diagnostics only (results invalid): 1 skip halo pull, 2 also skip the cross-GPU all-reduce
   long long poll_chunk = 0;   // 0: automatic
-  long long use_graph = 1;
   // sampled SpMV timing (bench.py roofline): event pairs around every Nth launch
   static constexpr int kSpmvPairs = 512;
   long long spmv_sample = 0, spmv_seen = 0;
@@ -144,6 +148,7 @@ struct Ctx {
 Ctx &ctx();
 int ensure_init();                   // PSP_OK or error; lazily initialises device 0
 int ensure_stage(size_t elems);      // pinned staging buffer of at least `elems` doubles
+int pool_get(int slot, size_t elems, double **out);   // context-owned device scratch (grows, never shrinks below use)
 
 // The matrix is streamed once per product, the vectors are re-used: when the vectors of
 // the problem (<= 3 M rows: 6 vectors <= 144 MB) can live in the 126 MB L2, the TMA loads

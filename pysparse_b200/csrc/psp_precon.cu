@@ -589,6 +589,14 @@ extern "C" int psp_ssor_create(psp_mat *sss, double omega, int steps, psp_prec *
   return ssor_create(sss, omega, steps, out);
 }
 
+extern "C" int psp_prec_set_matrix(psp_prec *K, psp_mat *A) {
+  if (!K || !A) { set_error("psp_prec_set_matrix: NULL argument"); return PSP_ERR_ARG; }
+  if (K->kind != 1) { set_error("psp_prec_set_matrix: only Jacobi preconditioners re-bind their matrix"); return PSP_ERR_ARG; }
+  if (A->m != K->n || A->n != K->n) { set_error("psp_prec_set_matrix: matrix order differs from the preconditioner's"); return PSP_ERR_ARG; }
+  K->mat = A;
+  return PSP_OK;
+}
+
 extern "C" void psp_prec_destroy(psp_prec *K) {
   if (!K) return;
   cudaFree(K->d_dinv); cudaFree(K->d_t1); cudaFree(K->d_t2);

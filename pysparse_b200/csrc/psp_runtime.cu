@@ -88,6 +88,24 @@ int ensure_stage(size_t elems) {
   return PSP_OK;
 }
 
+int pool_get(int slot, size_t elems, double **out) {
+  Ctx &c = g_ctx;
+  if (elems == 0) elems = 1;
+  if (c.pool_cap[slot] < elems || c.pool_cap[slot] > 4 * elems + (1u << 20)) {   // grow, or give back a much larger block
+    if (c.pool[slot]) cudaFree(c.pool[slot]);
+    c.pool[slot] = nullptr; c.pool_cap[slot] = 0;
+    cudaError_t e = cudaMalloc((void **)&c.pool[slot], sizeof(double) * elems);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      set_error("cudaMalloc(%zu doubles) failed: %s", elems, cudaGetErrorString(e));
+      return PSP_ERR_NOMEM;
+    }
+    c.pool_cap[slot] = elems;
+  }
+  *out = c.pool[slot];
+  return PSP_OK;
+}
+
 __global__ void k_fill(double *p, size_t n, double v) {
   size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
@@ -236,7 +254,6 @@ extern "C" int psp_set_option(const char *name, long long value) {
   if (!strcmp(name, "spmv_variant")) c.spmv_variant = value;
   else if (!strcmp(name, "spmv_ctas")) c.spmv_ctas = value;
   else if (!strcmp(name, "poll_chunk")) c.poll_chunk = value;
-  else if (!strcmp(name, "use_graph")) c.use_graph = value;
   else if (!strcmp(name, "l2_stream")) c.l2_stream = value;
   else if (!strcmp(name, "pcg_persist")) c.pcg_persist = value;
   else if (!strcmp(name, "ssor_engine")) c.ssor_engine = value;
@@ -255,7 +272,6 @@ extern "C" long long psp_get_option(const char *name) {
   if (!strcmp(name, "spmv_variant")) return c.spmv_variant;
   if (!strcmp(name, "spmv_ctas")) return c.spmv_ctas;
   if (!strcmp(name, "poll_chunk")) return c.poll_chunk;
-  if (!strcmp(name, "use_graph")) return c.use_graph;
   if (!strcmp(name, "sms")) return c.sms;
   if (!strcmp(name, "l2_stream")) return c.l2_stream;
   if (!strcmp(name, "pcg_persist")) return c.pcg_persist;

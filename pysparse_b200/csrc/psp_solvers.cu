@@ -770,9 +770,69 @@ static size_t work_vectors(int solver) {
   }
 }
 
+// Per-solve resources of the context (device State + the small block behind it, its pinned
+// mirror, the timing / polling events).  The outermost solve uses the ones created by
+// psp_init; a solve started from inside a Python operator callback of a running solve (inner-
+// outer iterations: a preconditioner that itself calls krylov.*) gets fresh ones, swapped into
+// the context for its duration, so that it cannot overwrite the outer solve's state -- the
+// reference's solvers are re-entrant C functions and support this.
+struct SolveFrame {
+  State *state = nullptr, *h_state = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evpoll[2] = {nullptr, nullptr};
+  void take(Ctx &c) { state = c.state; h_state = c.h_state; ev0 = c.ev0; ev1 = c.ev1; evpoll[0] = c.evpoll[0]; evpoll[1] = c.evpoll[1]; }
+  void put(Ctx &c) const { c.state = state; c.h_state = h_state; c.ev0 = ev0; c.ev1 = ev1; c.evpoll[0] = evpoll[0]; c.evpoll[1] = evpoll[1]; }
+  int create() {
+    PSP_CUDA(cudaMalloc((void **)&state, sizeof(State) + 256));
+    PSP_CUDA(cudaMemset(state, 0, sizeof(State) + 256));
+    PSP_CUDA(cudaHostAlloc((void **)&h_state, 2 * sizeof(State), cudaHostAllocDefault));
+    PSP_CUDA(cudaEventCreate(&ev0));
+    PSP_CUDA(cudaEventCreate(&ev1));
+    PSP_CUDA(cudaEventCreateWithFlags(&evpoll[0], cudaEventDisableTiming));
+    PSP_CUDA(cudaEventCreateWithFlags(&evpoll[1], cudaEventDisableTiming));
+    return PSP_OK;
+  }
+  void destroy() {
+    cudaFree(state); cudaFreeHost(h_state);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (evpoll[0]) cudaEventDestroy(evpoll[0]);
+    if (evpoll[1]) cudaEventDestroy(evpoll[1]);
+  }
+};
+
+static int solve_dev_frame(int solver, const psp_operator *Aop, const psp_operator *Kop, int n, const double *db,
+                           double *dx, double tol, int maxit, int gmres_dim, int *info, int *iter, double *relres);
+
 int solve_dev(int solver, const psp_operator *Aop, const psp_operator *Kop, int n, const double *db,
               double *dx, double tol, int maxit, int gmres_dim, int *info, int *iter, double *relres) {
   PSP_TRY(ensure_init());
+  Ctx &c = ctx();
+  if (c.solve_depth == 0) {
+    c.solve_depth = 1;
+    const int st = solve_dev_frame(solver, Aop, Kop, n, db, dx, tol, maxit, gmres_dim, info, iter, relres);
+    c.solve_depth = 0;
+    return st;
+  }
+  // nested solve: private frame
+  SolveFrame outer, inner;
+  outer.take(c);
+  int st = inner.create();
+  if (st == PSP_OK) {
+    const double outer_ms = c.last_ms;
+    inner.put(c);
+    c.solve_depth++;
+    st = solve_dev_frame(solver, Aop, Kop, n, db, dx, tol, maxit, gmres_dim, info, iter, relres);
+    c.solve_depth--;
+    cudaStreamSynchronize(c.stream);
+    outer.put(c);
+    c.last_ms = outer_ms;
+  }
+  inner.destroy();
+  return st;
+}
+
+static int solve_dev_frame(int solver, const psp_operator *Aop, const psp_operator *Kop, int n, const double *db,
+                           double *dx, double tol, int maxit, int gmres_dim, int *info, int *iter, double *relres) {
   Ctx &c = ctx();
   if (solver < 0 || solver > PSP_GMRES) { set_error("unknown solver id %d", solver); return PSP_ERR_ARG; }
   if (n < 0 || !Aop) { set_error("psp_solve: bad arguments"); return PSP_ERR_ARG; }
@@ -791,8 +851,11 @@ int solve_dev(int solver, const psp_operator *Aop, const psp_operator *Kop, int 
 
   double *work = nullptr;
   size_t nw = work_vectors(solver);
+  const bool pooled = (c.solve_depth == 1);       // nested solves must not share the outer solve's scratch
   if (nw) {
-    if (cudaMalloc((void **)&work, sizeof(double) * nw * (size_t)(n > 0 ? n : 1)) != cudaSuccess) {
+    const size_t elems = nw * (size_t)(n > 0 ? n : 1);
+    if (pooled) PSP_TRY(pool_get(2, elems, &work));
+    else if (cudaMalloc((void **)&work, sizeof(double) * elems) != cudaSuccess) {
       cudaGetLastError();
       set_error("psp_solve: out of device memory for %zu work vectors of length %d", nw, n);
       return PSP_ERR_NOMEM;
@@ -802,7 +865,8 @@ int solve_dev(int solver, const psp_operator *Aop, const psp_operator *Kop, int 
     if (cudaHostAlloc((void **)&s.hx, sizeof(double) * (size_t)(n > 0 ? n : 1), cudaHostAllocDefault) != cudaSuccess ||
         cudaHostAlloc((void **)&s.hy, sizeof(double) * (size_t)(n > 0 ? n : 1), cudaHostAllocDefault) != cudaSuccess) {
       cudaGetLastError();
-      cudaFree(work); cudaFreeHost(s.hx); cudaFreeHost(s.hy);
+      if (!pooled) cudaFree(work);
+      cudaFreeHost(s.hx); cudaFreeHost(s.hy);
       set_error("psp_solve: out of pinned host memory");
       return PSP_ERR_NOMEM;
     }
@@ -837,7 +901,7 @@ int solve_dev(int solver, const psp_operator *Aop, const psp_operator *Kop, int 
   };
   st = go();
   if (st != PSP_OK) cudaStreamSynchronize(c.stream);
-  cudaFree(work);
+  if (!pooled) cudaFree(work);
   if (s.hx) cudaFreeHost(s.hx);
   if (s.hy) cudaFreeHost(s.hy);
   if (st != PSP_OK) return st;
@@ -926,13 +990,19 @@ extern "C" int psp_solve(int solver, const psp_operator *A, const psp_operator *
   if (n < 0 || (n > 0 && (!b || !x))) { set_error("psp_solve: NULL vector"); return PSP_ERR_ARG; }
   PSP_TRY(ensure_init());
   double *db = nullptr, *dx = nullptr;
-  PSP_TRY(psp_vec_alloc((size_t)n, &db));
-  int st = psp_vec_alloc((size_t)n, &dx);
-  if (st == PSP_OK) st = psp_vec_upload(db, b, (size_t)n, 1);
+  const bool pooled = (ctx().solve_depth == 0);
+  if (pooled) {
+    PSP_TRY(pool_get(0, (size_t)n, &db));
+    PSP_TRY(pool_get(1, (size_t)n, &dx));
+  } else {
+    PSP_TRY(psp_vec_alloc((size_t)n, &db));
+    int sa = psp_vec_alloc((size_t)n, &dx);
+    if (sa != PSP_OK) { psp_vec_free(db); return sa; }
+  }
+  int st = psp_vec_upload(db, b, (size_t)n, 1);
   if (st == PSP_OK) st = psp_vec_upload(dx, x, (size_t)n, 1);
   if (st == PSP_OK) st = solve_dev(solver, A, K, n, db, dx, tol, maxit, gmres_dim, info, iter, relres);
   if (st == PSP_OK) st = psp_vec_download(dx, x, (size_t)n, 1);
-  psp_vec_free(db);
-  psp_vec_free(dx);
+  if (!pooled) { psp_vec_free(db); psp_vec_free(dx); }
   return st;
 }

@@ -33,10 +33,31 @@ static void Precon_dealloc(PreconObject *self)
   PyObject_Del(self);
 }
 
+static psp_mat *matrix_handle(PyObject *matrix, int *failed);
+
+/* A multi-step Jacobi preconditioner multiplies with its matrix.  The device copy of an
+ * ll_mat is rebuilt (and the old handle destroyed) whenever the matrix has been modified, so
+ * the handle is looked up again before every use instead of being cached at construction
+ * (the reference, too, calls the live matrix: preconmodule.c:45-52). */
+static int refresh_matrix(PreconObject *self)
+{
+  if (Py_TYPE(self) != &JacobiType || self->steps <= 1) return 0;
+  int failed;
+  psp_mat *h = matrix_handle(self->matrix, &failed);
+  if (!h) {
+    if (!failed) PyErr_SetString(PyExc_RuntimeError, "jacobi: the matrix has no device handle any more");
+    return -1;
+  }
+  int st = psp_prec_set_matrix(self->dev, h);
+  if (st != PSP_OK) { psp_raise(st); return -1; }
+  return 0;
+}
+
 static PyObject *Precon_precon(PreconObject *self, PyObject *args)
 {
   double *x, *y;
   if (((int (*)(PyObject *, double **, double **, int))SpMatrix_API[PSP_API_ParseVecOpArgs])(args, &x, &y, self->n)) return NULL;
+  if (refresh_matrix(self)) return NULL;
   int st = psp_prec_apply(self->dev, x, y);
   if (st != PSP_OK) return psp_raise(st);
   Py_RETURN_NONE;
@@ -44,7 +65,11 @@ static PyObject *Precon_precon(PreconObject *self, PyObject *args)
 
 static void cap_noop(PyObject *c) { (void)c; }
 static PyObject *Precon_get_shape(PreconObject *self, void *c) { return Py_BuildValue("(i,i)", self->n, self->n); }
-static PyObject *Precon_get_dev(PreconObject *self, void *c) { return PyCapsule_New(self->dev, PSP_PREC_CAPSULE, cap_noop); }
+static PyObject *Precon_get_dev(PreconObject *self, void *c)
+{
+  if (refresh_matrix(self)) return NULL;        /* krylov reads this attribute at the start of every solve */
+  return PyCapsule_New(self->dev, PSP_PREC_CAPSULE, cap_noop);
+}
 static PyObject *Precon_get_levels(PreconObject *self, void *c)
 {
   int nf = 0, nb = 0;

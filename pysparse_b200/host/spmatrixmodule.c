@@ -593,6 +593,10 @@ static PyObject *put_like(LLMatObject *self, PyObject *args, int add)
     double v = b_scalar ? bv[0] : bv[k];
     if (r < 0) r += self->dim[0];
     if (c < 0) c += self->dim[1];
+    if (r < 0 || r >= self->dim[0] || c < 0 || c >= self->dim[1]) {   /* checked as long: no 2^31 wrap-around */
+      PyErr_SetString(PyExc_IndexError, "indices out of range");
+      goto done;
+    }
     int rc = add ? SpMatrix_LLMatUpdateItemAdd(self, (int)r, (int)c, v) : SpMatrix_LLMatSetItem(self, (int)r, (int)c, v);
     if (rc) goto done;
   }
@@ -642,6 +646,10 @@ static PyObject *LLMat_take(LLMatObject *self, PyObject *args)
     long r = p1 ? p1[k] : k, c = p2 ? p2[k] : r;
     if (r < 0) r += self->dim[0];
     if (c < 0) c += self->dim[1];
+    if (r < 0 || r >= self->dim[0] || c < 0 || c >= self->dim[1]) {
+      PyErr_SetString(PyExc_IndexError, "indices out of range");
+      goto done;
+    }
     bv[k] = SpMatrix_LLMatGetItem(self, (int)r, (int)c);
     if (PyErr_Occurred()) goto done;
   }
@@ -1520,7 +1528,45 @@ static PyObject *LLMat_from_mtx(PyObject *self, PyObject *args)
 }
 
 /* ---- pysparse_b200 additions: build csr_mat / sss_mat straight from arrays -- */
-static PyArrayObject *want(PyObject *o, int type) { return (PyArrayObject *)PyArray_FROM_OTF(o, type, NPY_ARRAY_IN_ARRAY); }
+/* A private, C-contiguous copy of `o` as float64 / int32.  Integer arrays of any width are
+ * accepted (NumPy's default int64 included) after an explicit range check; the copy means later
+ * edits of the caller's arrays cannot desynchronise the host data from the cached device copy. */
+static PyArrayObject *want(PyObject *o, int type)
+{
+  if (type == NPY_DOUBLE) return (PyArrayObject *)PyArray_FROM_OTF(o, NPY_DOUBLE, NPY_ARRAY_IN_ARRAY | NPY_ARRAY_ENSURECOPY);
+  if (PyArray_Check(o) && PyArray_TYPE((PyArrayObject *)o) == NPY_INT32)        /* already narrow: plain copy, */
+    return (PyArrayObject *)PyArray_FROM_OTF(o, NPY_INT32, NPY_ARRAY_IN_ARRAY | NPY_ARRAY_ENSURECOPY);   /* range checked by structure_ok */
+  PyArrayObject *wide = (PyArrayObject *)PyArray_FROM_OTF(o, NPY_INT64, NPY_ARRAY_IN_ARRAY);
+  if (!wide) return NULL;
+  const npy_int64 *w = (const npy_int64 *)PyArray_DATA(wide);
+  const npy_intp len = PyArray_SIZE(wide);
+  for (npy_intp k = 0; k < len; k++)
+    if (w[k] < 0 || w[k] > 2147483647LL) {
+      Py_DECREF(wide);
+      PyErr_SetString(PyExc_ValueError, "index array holds values outside [0, 2^31)");
+      return NULL;
+    }
+  PyArrayObject *out = (PyArrayObject *)PyArray_Cast(wide, NPY_INT32);
+  Py_DECREF(wide);
+  if (out && !PyArray_ISCARRAY(out)) { Py_DECREF(out); PyErr_SetString(PyExc_ValueError, "index array conversion failed"); return NULL; }
+  return out;
+}
+
+/* the check the device upload would make, done at construction so that A[i,j], diagonal() ...
+ * never read outside the arrays: monotone row pointers, column range, strict lower triangle */
+static int structure_ok(int m, int n, const int *ind, const int *col, npy_intp nnz, int strict_lower, const char *who)
+{
+  if (m < 0 || n < 0 || ind[0] != 0 || ind[m] != nnz) { PyErr_Format(PyExc_ValueError, "%s: ind[0] != 0 or ind[m] != nnz", who); return 0; }
+  for (int i = 0; i < m; i++) {
+    if (ind[i + 1] < ind[i]) { PyErr_Format(PyExc_ValueError, "%s: row pointer array not monotone at row %d", who, i); return 0; }
+    for (int k = ind[i]; k < ind[i + 1]; k++)
+      if (col[k] < 0 || col[k] >= n || (strict_lower && col[k] >= i)) {
+        PyErr_Format(PyExc_ValueError, "%s: column index %d out of range in row %d", who, col[k], i);
+        return 0;
+      }
+  }
+  return 1;
+}
 
 static PyObject *csr_from_arrays(PyObject *self, PyObject *args)
 {
@@ -1531,6 +1577,10 @@ static PyObject *csr_from_arrays(PyObject *self, PyObject *args)
   if (PyArray_SIZE(ind) != (npy_intp)m + 1 || PyArray_SIZE(col) != PyArray_SIZE(val)) {
     Py_DECREF(ind); Py_DECREF(col); Py_DECREF(val);
     PyErr_SetString(PyExc_ValueError, "csr_from_arrays: inconsistent array lengths");
+    return NULL;
+  }
+  if (!structure_ok(m, n, (const int *)PyArray_DATA(ind), (const int *)PyArray_DATA(col), PyArray_SIZE(val), 0, "csr_from_arrays")) {
+    Py_DECREF(ind); Py_DECREF(col); Py_DECREF(val);
     return NULL;
   }
   CSRMatObject *op = PyObject_New(CSRMatObject, &CSRMatType);
@@ -1551,6 +1601,10 @@ static PyObject *sss_from_arrays(PyObject *self, PyObject *args)
   if (PyArray_SIZE(ind) != (npy_intp)n + 1 || PyArray_SIZE(col) != PyArray_SIZE(val) || PyArray_SIZE(diag) != n) {
     Py_DECREF(ind); Py_DECREF(col); Py_DECREF(val); Py_DECREF(diag);
     PyErr_SetString(PyExc_ValueError, "sss_from_arrays: inconsistent array lengths");
+    return NULL;
+  }
+  if (!structure_ok(n, n, (const int *)PyArray_DATA(ind), (const int *)PyArray_DATA(col), PyArray_SIZE(val), 1, "sss_from_arrays")) {
+    Py_DECREF(ind); Py_DECREF(col); Py_DECREF(val); Py_DECREF(diag);
     return NULL;
   }
   SSSMatObject *op = PyObject_New(SSSMatObject, &SSSMatType);

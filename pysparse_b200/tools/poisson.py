@@ -9,74 +9,66 @@ import numpy as np
 from ..sparse import spmatrix
 
 
-def poisson1d(n):
-    L = spmatrix.ll_mat(n, n, 3 * n - 2)
-    for i in range(n):
-        L[i, i] = 2
-        if i > 0:
-            L[i, i - 1] = -1
-        if i < n - 1:
-            L[i, i + 1] = -1
+def _laplacian_triples(shape, lower_only):
+    """Yield (row, col, value) of the (2d+1)-point Laplacian on a lexicographically numbered
+    grid of extents ``shape`` (first index fastest): the diagonal 2d first, then the couplings to
+    the lower / upper neighbour along each axis, row after row."""
+    dims = len(shape)
+    strides = [int(np.prod(shape[:a], dtype=np.int64)) for a in range(dims)]
+    for idx in np.ndindex(*reversed(shape)):
+        pos = idx[::-1]                                   # pos[a]: coordinate along axis a
+        row = sum(c * s for c, s in zip(pos, strides))
+        yield row, row, 2.0 * dims
+        for a in range(dims):
+            if pos[a] > 0:
+                yield row, row - strides[a], -1.0
+            if not lower_only and pos[a] < shape[a] - 1:
+                yield row, row + strides[a], -1.0
+
+
+def _assign_elementwise(L, triples):
+    "one ``L[i, j] = v`` per entry: the slow path the reference's generators exercise"
+    for i, j, v in triples:
+        L[i, j] = v
     return L
+
+
+def poisson1d(n):
+    return _assign_elementwise(spmatrix.ll_mat(n, n, 3 * n - 2), _laplacian_triples((n,), False))
 
 
 def poisson1d_sym(n):
-    L = spmatrix.ll_mat_sym(n, 2 * n - 1)
-    for i in range(n):
-        L[i, i] = 2
-        if i > 0:
-            L[i, i - 1] = -1
-    return L
+    return _assign_elementwise(spmatrix.ll_mat_sym(n, 2 * n - 1), _laplacian_triples((n,), True))
 
 
 def poisson2d(n):
-    n2 = n * n
-    L = spmatrix.ll_mat(n2, n2, 5 * n2 - 4 * n)
-    for i in range(n):
-        for j in range(n):
-            k = i + n * j
-            L[k, k] = 4
-            if i > 0:
-                L[k, k - 1] = -1
-            if i < n - 1:
-                L[k, k + 1] = -1
-            if j > 0:
-                L[k, k - n] = -1
-            if j < n - 1:
-                L[k, k + n] = -1
-    return L
+    return _assign_elementwise(spmatrix.ll_mat(n * n, n * n, 5 * n * n - 4 * n), _laplacian_triples((n, n), False))
 
 
 def poisson2d_sym(n):
-    n2 = n * n
-    L = spmatrix.ll_mat_sym(n2, 3 * n2 - 2 * n)
-    for i in range(n):
-        for j in range(n):
-            k = i + n * j
-            L[k, k] = 4
-            if i > 0:
-                L[k, k - 1] = -1
-            if j > 0:
-                L[k, k - n] = -1
-    return L
+    return _assign_elementwise(spmatrix.ll_mat_sym(n * n, 3 * n * n - 2 * n), _laplacian_triples((n, n), True))
 
 
 def poisson2d_sym_blk(n):
-    n2 = n * n
-    L = spmatrix.ll_mat_sym(n2, 3 * n2 - 2 * n)
-    I = spmatrix.ll_mat_sym(n, n)
-    for i in range(n):
-        I[i, i] = -1
-    P = spmatrix.ll_mat_sym(n, 2 * n - 1)
-    for i in range(n):
-        P[i, i] = 4
-        if i > 0:
-            P[i, i - 1] = -1
-    for i in range(0, n * n, n):
-        L[i:i + n, i:i + n] = P
-        if i > 0:
-            L[i:i + n, i - n:i] = I
+    "block-wise assembly through slice assignment: tridiagonal blocks T, coupling blocks -I"
+    L = spmatrix.ll_mat_sym(n * n, 3 * n * n - 2 * n)
+    T = poisson1d_sym(n)
+    T.shift(2.0, _identity_sym(n))                        # 1-D stencil (2, -1) -> (4, -1)
+    minus_I = _identity_sym(n)
+    minus_I.scale(-1.0)
+    for blk in range(n):
+        lo, hi = blk * n, (blk + 1) * n
+        L[lo:hi, lo:hi] = T
+        if blk:
+            L[lo:hi, lo - n:lo] = minus_I
     return L
+
+
+def _identity_sym(n):
+    eye = spmatrix.ll_mat_sym(n, n)
+    d = np.arange(n, dtype=np.int64)
+    eye.put(np.ones(n), d, d)
+    return eye
 
 
 def poisson1d_vec(n):

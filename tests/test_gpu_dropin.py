@@ -329,3 +329,63 @@ def test_jdsym_reference_cases_on_the_gpu_path(mods):
     T = 2 * np.eye(12) - np.eye(12, k=1) - np.eye(12, k=-1)
     w = np.linalg.eigvalsh(np.kron(np.eye(12), T) + np.kron(T, np.eye(12)))
     assert kconv == 4 and np.allclose(np.sort(lam), w[:4], rtol=0, atol=1e-7)
+
+
+def test_inner_outer_iteration_through_a_python_preconditioner(mods):
+    """A preconditioner object whose precon() itself calls krylov.* (inner-outer iteration): the
+    reference's solvers are re-entrant C functions (itsolversmodule.c:32-117 allocate per call);
+    here the nested solve must get its own device state and leave the outer solve untouched."""
+    spmatrix, krylov, precon, poisson = mods
+    L = poisson.poisson2d_sym_vec(40)
+    S = L.to_sss()
+    n = 1600
+    b = np.ones(n)
+
+    class InnerSolve:
+        shape = (n, n)
+        calls = 0
+
+        def precon(self, x, y):
+            y[:] = 0.0
+            info, it, rr = krylov.pcg(S, x.copy(), y, 1e-3, 50)      # nested solve on the same device context
+            assert info in (0, -1)
+            InnerSolve.calls += 1
+
+    x = np.zeros(n)
+    info, it, relres = krylov.gmres(S, b, x, 1e-9, 200, InnerSolve(), 20)
+    assert info == 0 and InnerSolve.calls >= it >= 1
+    r = np.empty(n); S.matvec(x, r)
+    assert np.linalg.norm(b - r) <= 1e-8 * np.linalg.norm(b)
+    # and a plain solve afterwards is unaffected by the frames that were swapped in and out
+    x2 = np.zeros(n)
+    k = krylov.pcg(S, b, x2, 1e-10, 2000)
+    x3 = np.zeros(n)
+    assert krylov.pcg(S, b, x3, 1e-10, 2000) == k and np.array_equal(x2, x3)
+
+
+def test_multistep_jacobi_follows_an_edited_llmat(mods, checker):
+    """precon.jacobi(A, omega, steps > 1) multiplies with A at every application
+    (preconmodule.c:45-52).  Editing the ll_mat afterwards rebuilds its device copy; the
+    preconditioner must use the new copy, not a dangling handle to the old one."""
+    spmatrix, krylov, precon, poisson = mods
+    n = 30
+    L = poisson.poisson2d_vec(n)
+    K = precon.jacobi(L, 0.9, 3)                  # dinv is frozen here (newJacobiObject, :389-401)
+    x = np.linspace(-1.0, 1.0, n * n)
+    y0 = np.empty(n * n); K.precon(x, y0)
+    L[5, 5] = 7.5                                 # invalidates the cached device matrix
+    L[0, n * n - 1] = -0.25
+    y1 = np.empty(n * n); K.precon(x, y1)
+    # model: damped Jacobi sweeps with the OLD diagonal and the NEW matrix
+    dinv = 0.9 / 4.0
+    A = L.to_csr()
+    ym = x * dinv
+    t = np.empty(n * n)
+    for _ in range(2):
+        A.matvec(ym, t)
+        ym = (x - t) * dinv + ym
+    assert np.max(np.abs(y1 - ym)) <= 1e-13 * np.max(np.abs(ym))
+    assert not np.array_equal(y0, y1)
+    xs = np.zeros(n * n)
+    info, it, rr = krylov.pcg(L, np.ones(n * n), xs, 1e-8, 500, K)     # krylov re-reads K's handle too
+    assert info in (0, -1)

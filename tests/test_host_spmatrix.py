@@ -220,3 +220,39 @@ def test_no_gpu_means_loud_failure_not_cpu_fallback(mods, native):
         krylov.pcg(L.to_csr(), np.ones(16), np.zeros(16), 1e-8, 10)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         precon.jacobi(L)
+
+
+def test_from_arrays_accepts_wide_indices_validates_and_copies():
+    """csr_from_arrays / sss_from_arrays: NumPy's default int64 index arrays are accepted after a
+    range check, malformed structure is refused at construction, and the arrays are copied."""
+    from pysparse_b200.sparse import spmatrix
+    ind = np.array([0, 2, 3], dtype=np.int64)
+    col = np.array([0, 1, 1], dtype=np.int64)
+    val = np.array([1.0, 2.0, 3.0])
+    A = spmatrix.csr_from_arrays(2, 2, ind, col, val)
+    val[0] = 99.0; col[0] = 1                      # later edits of the caller's arrays do not reach A
+    assert A[0, 0] == 1.0 and A[0, 1] == 2.0 and A[1, 1] == 3.0 and A.nnz == 3
+    with pytest.raises(ValueError):
+        spmatrix.csr_from_arrays(2, 2, np.array([0, 2, 3]), np.array([0, 2**31 + 1, 1]), val)
+    with pytest.raises(ValueError):
+        spmatrix.csr_from_arrays(2, 2, np.array([0, 2, 3]), np.array([0, 5, 1]), val)       # column out of range
+    with pytest.raises(ValueError):
+        spmatrix.csr_from_arrays(2, 2, np.array([0, 3, 2]), np.array([0, 1, 1]), val)       # not monotone
+    with pytest.raises(ValueError):
+        spmatrix.sss_from_arrays(2, np.array([0, 0, 1]), np.array([1]), np.array([1.0]), np.ones(2))   # not strictly lower
+    S = spmatrix.sss_from_arrays(2, np.array([0, 0, 1]), np.array([0]), np.array([-1.0]), np.full(2, 4.0))
+    assert S[1, 0] == -1.0 and S[0, 1] == -1.0 and S[1, 1] == 4.0
+
+
+def test_index_arrays_beyond_int32_raise_instead_of_wrapping():
+    from pysparse_b200.sparse import spmatrix
+    A = spmatrix.ll_mat(3, 3)
+    A[1, 0] = 5.0
+    out = np.zeros(1)
+    with pytest.raises(IndexError):
+        A.take(out, np.array([2**32 + 1]), np.array([0]))
+    with pytest.raises(IndexError):
+        A.put(np.array([1.0]), np.array([2**32 + 1]), np.array([0]))
+    with pytest.raises(IndexError):
+        A.update_add_at(np.array([1.0]), np.array([0]), np.array([2**32 + 2]))
+    assert A[1, 0] == 5.0 and A.nnz == 1
