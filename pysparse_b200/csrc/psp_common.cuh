@@ -126,6 +126,10 @@ struct Ctx {
   size_t pool_cap[3] = {0, 0, 0};
   // options
   long long spmv_variant = 0;
+  long long spmv_format = -1; // device layout chosen at matrix creation: -1 automatic, 0 CSR row blocks, 1 diagonal runs
+  int occ_runs[2] = {0, 0};   // resident CTAs of k_spmv_runs<false/true> on this device
+  int occ_pcg[2] = {0, 0};    // resident CTAs of k_pcg_persist<format> on this device
+  int occ_bicg[2] = {0, 0}, occ_gmres[2] = {0, 0};
   long long spmv_ctas = 0;    // cap on resident CTAs per SM for the TMA SpMV (0: occupancy limit)
   long long l2_stream = -1;   // L2 evict-first hint on the matrix stream: 1 on, 0 off, -1 automatic
   long long pcg_persist = -1; // single-launch PCG: 1 always, 0 never, -1 automatic

@@ -188,7 +188,7 @@ extern "C" int psp_dist_info(int *rank, int *world, size_t *slot_elems, int *nsl
 
 // ------------------------------------------------------------------ distributed matrix
 namespace psp {
-int csr_create(int, int, long long, const int *, const int *, const double *, psp_mat **, bool, int);
+int csr_create(int, int, long long, const int *, const int *, const double *, psp_mat **, bool, int, const int *, int);
 }
 
 extern "C" int psp_dist_csr_create(const int *rowptr, int nnz, const int *ind, const int *col_global,
@@ -208,7 +208,7 @@ extern "C" int psp_dist_csr_create(const int *rowptr, int nnz, const int *ind, c
   }
   DistMat *dm = new DistMat();
   dm->nl = nl; dm->nhalo = nhalo; dm->nglobal = rowptr[d.world];
-  int st = csr_create(nl, nl + nhalo, nnz, ind, col_local.data(), val, &dm->local, false, nl);
+  int st = csr_create(nl, nl + nhalo, nnz, ind, col_local.data(), val, &dm->local, false, nl, col_global, rowptr[d.rank]);
   if (st != PSP_OK) { delete dm; return st; }
   dm->nbmask = 0;
   for (int h = 0; h < nhalo; h++) dm->nbmask |= 1u << owner[h];

@@ -18,9 +18,17 @@ struct psp_mat {
   int nint = 0;             // leading blocks that read no halo column (== nb unless sharded)
   int *d_blk = nullptr;
   int *d_blk_halo = nullptr; // sharded slabs: per block, [first, end) of the halo positions it reads (int2)
-  // SSS originals (strict lower CSR + diagonal), kept for the SSOR sweeps
-  int *d_lind = nullptr, *d_lcol = nullptr;
-  double *d_lval = nullptr, *d_diag = nullptr;
+  // "diagonal run" format (psp_runs.cuh), chosen by the analysis at creation when the runs are
+  // long: fmt == 1, the CSR arrays above are then NOT on the device (d_ind/d_col/d_val stay
+  // nullptr) and nb / nint describe the run blocks.  SSS: d_diag points into d_rval.
+  int fmt = 0;
+  double *d_rval = nullptr;
+  int *d_rseg = nullptr, *d_rblk = nullptr;
+  long long rval_len = 0;   // doubles in d_rval
+  int nseg = 0;
+  // SSS: the diagonal on the device (the SSOR sweeps read it; their level-major copies of the
+  // lower triangle are built from the host arrays below)
+  double *d_diag = nullptr;
   // host copy of the SSS structure (level analysis) / CSR structure (transpose)
   std::vector<int> h_ind, h_col;
   std::vector<double> h_val, h_diag;
@@ -70,6 +78,21 @@ struct SpmvDots {
 };
 
 int spmv_launch(const psp_mat *a, const double *dx, double *dy, const SpmvDots &dots);
+int runs_launch(const psp_mat *a, const double *dx, double *dy, const SpmvDots &dots);   // psp_runs.cu
+// blocks per chunk of the run pass: as many as keep every resident CTA supplied with >= 2 chunks
+inline int run_chunk(int nb, int resident_ctas) {
+  int c = resident_ctas > 0 ? nb / (2 * resident_ctas) : 1;
+  return c < 1 ? 1 : (c > 8 ? 8 : c);
+}
+// analysis + upload of the run format; *accepted = false leaves A untouched (psp_runs.cu).
+// gcol / grow0: global column of every entry and global index of row 0 (row slabs of sharded
+// matrices: the runs are ordered by GLOBAL diagonal so that a slab adds in the same order as
+// the unsharded matrix); own_cols >= 0: columns >= own_cols are halo columns.
+int runs_try_csr(psp_mat *A, const int *ind, const int *col, const double *val, const int *gcol, int grow0,
+                 int own_cols, bool *accepted);
+int runs_try_sss(psp_mat *A, const int *ind, const int *col, const double *val, const double *diag, bool *accepted);
+// inverse of the analysis (CSR matrices): expand the device runs into host CSR arrays
+int runs_to_csr(const psp_mat *A, std::vector<int> &ind, std::vector<int> &col, std::vector<double> &val);
 int mat_transpose(psp_mat *a);     // builds a->transp lazily
 
 }  // namespace psp

@@ -35,13 +35,17 @@ struct PcgArgs : PersistArgs {
   const double *dinv;           // nullptr: identity preconditioner
 };
 
-__global__ void __launch_bounds__(kThreads, kPersistCtas) k_pcg_persist(PcgArgs a, size_t p_slot_off) {
+template <int FMT>
+__global__ void __launch_bounds__(kThreads, persist_ctas(FMT)) k_pcg_persist(PcgArgs a, size_t p_slot_off) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) uint64_t full[kPersistStages];
+  __shared__ __align__(8) uint64_t full[FMT == 0 ? kPersistStages : 1];
+  __shared__ __align__(16) unsigned char sseg_raw[FMT == 1 ? sizeof(RunSmem) : 16];   // (format 0 stages its descriptors in the TMA ring)
+  RunSmem *sseg = reinterpret_cast<RunSmem *>(sseg_raw);
   __shared__ double red_sh[8 * (kRedSlots + 1)];
   __shared__ double tot[kRedSlots + 1];
   __shared__ State sS;
   cg::grid_group grid = cg::this_grid();
+  constexpr int VU = vec_unroll(FMT);      // elements per thread and trip in the vector phases
   const int tid = threadIdx.x;
   // 32-bit indices: n < 2^31 and gridDim * blockDim < 2^20, so i + gstride cannot wrap
   const unsigned n = (unsigned)a.n;
@@ -59,9 +63,9 @@ __global__ void __launch_bounds__(kThreads, kPersistCtas) k_pcg_persist(PcgArgs 
   const bool push = c.dd && a.push;
   const bool do_push = push && c.debug < 1;
 
-  Ring<kPersistStages> ring;
-  ring.init(smem, full, a.l2_stream != 0);
-  ring.prefetch(a.A);
+  MatPass<FMT> ring;
+  ring.init(smem, full, a.l2_stream != 0, sseg);
+  ring.prefetch(a);
 
   // ---- ||b||  (pcg.c:57-67)
   {
@@ -89,13 +93,13 @@ __global__ void __launch_bounds__(kThreads, kPersistCtas) k_pcg_persist(PcgArgs 
     xin = p_cur;
   }
 #ifdef PSP_BLOCK_UNPACK
-  ring.template pass<false, true>(a.A, xin, red_sh, [&](int r, double sum) { a.r[r] = sum; },
+  ring.template pass<true>(a, xin, red_sh, [&](int r, double sum) { a.r[r] = sum; },
                                   [&](int b) { if (push) halo_unpack_block(c, a, p_cur, b); });
 #else
-  ring.template pass<false>(a.A, xin, red_sh, [&](int r, double sum) { a.r[r] = sum; },
+  ring.template pass<false>(a, xin, red_sh, [&](int r, double sum) { a.r[r] = sum; },
                             [&](int) { if (push) halo_wait(c, a); });
 #endif
-  ring.prefetch(a.A);
+  ring.prefetch(a);
   grid.sync();
   {
     double acc[2] = {0.0, 0.0};
@@ -130,10 +134,10 @@ __global__ void __launch_bounds__(kThreads, kPersistCtas) k_pcg_persist(PcgArgs 
           halo_send(c, a, s, first ? zi : zi + beta * p_cur[row]);
         }
       }
-      for (unsigned i0 = g0; i0 < n; i0 += kVecUnroll * gstride) {
-        double ri[kVecUnroll], di[kVecUnroll], pi[kVecUnroll];
+      for (unsigned i0 = g0; i0 < n; i0 += VU * gstride) {
+        double ri[VU], di[VU], pi[VU];
 #pragma unroll
-        for (int u = 0; u < kVecUnroll; u++) {
+        for (int u = 0; u < VU; u++) {
           const unsigned i = i0 + u * gstride;
           const bool ok = i < n;
           ri[u] = ok ? a.r[i] : 0.0;
@@ -141,7 +145,7 @@ __global__ void __launch_bounds__(kThreads, kPersistCtas) k_pcg_persist(PcgArgs 
           pi[u] = (ok && !first) ? p_cur[i] : 0.0;
         }
 #pragma unroll
-        for (int u = 0; u < kVecUnroll; u++) {
+        for (int u = 0; u < VU; u++) {
           const unsigned i = i0 + u * gstride;
           if (i < n) {
             const double zi = a.dinv ? ri[u] * di[u] : ri[u];
@@ -165,13 +169,13 @@ __global__ void __launch_bounds__(kThreads, kPersistCtas) k_pcg_persist(PcgArgs 
     {                                   // q = A p ; pq = p.q
       double acc[1] = {0.0};
 #ifdef PSP_BLOCK_UNPACK
-      ring.template pass<false, true>(a.A, p_new, red_sh, [&](int r, double sum) { a.q[r] = sum; acc[0] += p_new[r] * sum; },
+      ring.template pass<true>(a, p_new, red_sh, [&](int r, double sum) { a.q[r] = sum; acc[0] += p_new[r] * sum; },
                                       [&](int b) { if (push) halo_unpack_block(c, a, p_new, b); });
 #else
-      ring.template pass<false>(a.A, p_new, red_sh, [&](int r, double sum) { a.q[r] = sum; acc[0] += p_new[r] * sum; },
+      ring.template pass<false>(a, p_new, red_sh, [&](int r, double sum) { a.q[r] = sum; acc[0] += p_new[r] * sum; },
                                 [&](int) { if (push) { PROF_T(c, 3); halo_wait(c, a); PROF_T(c, 13); } });
 #endif
-      ring.prefetch(a.A);
+      ring.prefetch(a);
       PROF_T(c, 3);
       grid_allreduce<1, false>(c, a, acc, 0.0);
       PROF_T(c, 4);
@@ -183,10 +187,10 @@ __global__ void __launch_bounds__(kThreads, kPersistCtas) k_pcg_persist(PcgArgs 
       const double alpha = sS.v[V_ALPHA];
       const bool scan = (sS.stag == 0);
       double acc[2] = {0.0, 0.0}, mx = 0.0;
-      for (unsigned i0 = g0; i0 < n; i0 += kVecUnroll * gstride) {
-        double xv[kVecUnroll], pv[kVecUnroll], rv[kVecUnroll], qv[kVecUnroll], dv[kVecUnroll];
+      for (unsigned i0 = g0; i0 < n; i0 += VU * gstride) {
+        double xv[VU], pv[VU], rv[VU], qv[VU], dv[VU];
 #pragma unroll
-        for (int u = 0; u < kVecUnroll; u++) {
+        for (int u = 0; u < VU; u++) {
           const unsigned i = i0 + u * gstride;
           const bool ok = i < n;
           xv[u] = ok ? a.x[i] : 0.0;
@@ -196,7 +200,7 @@ __global__ void __launch_bounds__(kThreads, kPersistCtas) k_pcg_persist(PcgArgs 
           dv[u] = (ok && a.dinv) ? a.dinv[i] : 1.0;
         }
 #pragma unroll
-        for (int u = 0; u < kVecUnroll; u++) {
+        for (int u = 0; u < VU; u++) {
           const unsigned i = i0 + u * gstride;
           if (i < n) {
             const double xi = xv[u], pi = pv[u];
@@ -231,7 +235,7 @@ __global__ void __launch_bounds__(kThreads, kPersistCtas) k_pcg_persist(PcgArgs 
   }
 #endif
 
-  ring.drain(a.A);
+  ring.drain(a);
   if (blockIdx.x == 0 && tid == 0) {
     *a.S = sS;
     if (c.dd) {                       // 64-bit sequence numbers: add what this launch did (wrap-safe)
@@ -253,6 +257,9 @@ int persist_prepare(PersistArgs &a, const psp_mat *M, int n, DistMat *dm) {
   a.A.blk = reinterpret_cast<const int4 *>(M->d_blk);
   a.A.nint = M->nint;
   a.A.blk_halo = reinterpret_cast<const int2 *>(M->d_blk_halo);
+  a.R.val = M->d_rval; a.R.seg = reinterpret_cast<const int4 *>(M->d_rseg);
+  a.R.blk = reinterpret_cast<const int4 *>(M->d_rblk); a.R.nb = M->nb; a.R.nint = M->nint;
+  a.R.blk_halo = reinterpret_cast<const int2 *>(M->d_blk_halo);
   a.n = n;
   a.S = c.state; a.partials = g_partials2; a.sync = g_sync; a.dd = dm ? dist().dev : nullptr;
   a.l2_stream = l2_stream_for(n); a.dist_debug = (int)c.dist_debug;
@@ -274,13 +281,16 @@ int persist_grid(const psp_mat *M, int n, int resident) {
 int pcg_persist_launch(const psp_mat *M, int n, const double *b, double *x, double *r, double *p, double *p2,
                        double *q, const double *dinv, DistMat *dm) {
   Ctx &c = ctx();
-  static int resident = 0;
-  const int smem_bytes = kPersistStages * kStageBytes;
+  const int fmt = M->fmt;
+  const void *kern = fmt == 1 ? (const void *)k_pcg_persist<1> : (const void *)k_pcg_persist<0>;
+  const int smem_bytes = fmt == 1 ? 0 : kPersistStages * kStageBytes;
+  int &resident = c.occ_pcg[fmt];
   if (resident == 0) {
-    PSP_CUDA(cudaFuncSetAttribute(k_pcg_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    if (smem_bytes) PSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_persist, kThreads, smem_bytes) != cudaSuccess || per_sm < 1)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem_bytes) != cudaSuccess || per_sm < 1)
       per_sm = 1;
+    if (per_sm > persist_ctas(fmt)) per_sm = persist_ctas(fmt);
     resident = per_sm * c.sms;
     if (resident > kMaxGrid) resident = kMaxGrid;
   }
@@ -289,8 +299,9 @@ int pcg_persist_launch(const psp_mat *M, int n, const double *b, double *x, doub
   a.b = b; a.x = x; a.r = r; a.p = p; a.p2 = p2; a.q = q; a.dinv = dinv;
   size_t p_slot_off = dm ? (size_t)(p - dist().heap) : 0;
   const int grid = persist_grid(M, n, resident);
+  a.R.chunk = run_chunk(M->nb, grid);
   void *args[] = {&a, &p_slot_off};
-  PSP_CUDA(cudaLaunchCooperativeKernel((const void *)k_pcg_persist, dim3(grid), dim3(kThreads), args, smem_bytes, c.stream));
+  PSP_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kThreads), args, smem_bytes, c.stream));
   c.launches++;
   return PSP_OK;
 }

@@ -8,6 +8,7 @@
 #include "psp_mat.cuh"
 #include "psp_epilogue.cuh"
 #include "psp_tma_ring.cuh"
+#include "psp_runs.cuh"
 #include "psp_dist.cuh"
 
 namespace cg = cooperative_groups;
@@ -27,13 +28,31 @@ namespace psp {
 constexpr int kPersistStages = PSP_PERSIST_STAGES;   // TMA ring depth
 constexpr int kPersistCtas = PSP_PERSIST_CTAS;       // CTAs per SM the register budget is sized for
 constexpr int kVecUnroll = PSP_VEC_UNROLL;           // elements per thread and trip in the vector phases
+#ifndef PSP_PERSIST_RUN_UNROLL
+#define PSP_PERSIST_RUN_UNROLL 8
+#endif
+constexpr int kPersistRunUnroll = PSP_PERSIST_RUN_UNROLL;   // runs per memory round trip in the diagonal-run pass
+#ifndef PSP_PERSIST_RUN_CTAS
+#define PSP_PERSIST_RUN_CTAS 4
+#endif
+// CTAs per SM the register budget is sized for, by matrix format.  Measured at 256^3 (PCG +
+// Jacobi, it/s CSR / SSS): 4 CTAs x 64 registers, 8 runs per batch 2030 / 2163; 3 CTAs x 80
+// registers with 2 elements per thread in the vector phases 1976 / 2165; 2 CTAs x 128 registers
+// 1686 / 1852 (profiles/r2_runs_notes.md).
+__host__ __device__ constexpr int persist_ctas(int fmt) { return fmt == 1 ? PSP_PERSIST_RUN_CTAS : kPersistCtas; }
+#ifndef PSP_RUN_VEC_UNROLL
+#define PSP_RUN_VEC_UNROLL 1
+#endif
+// fewer resident threads (format 1) need more loads in flight per thread in the vector phases
+__host__ __device__ constexpr int vec_unroll(int fmt) { return fmt == 1 ? PSP_RUN_VEC_UNROLL : kVecUnroll; }
 
 struct PersistSync;
 
 // The part of a persistent solver's kernel arguments the shared helpers use (lives in the
 // parameter bank: costs no registers).
 struct PersistArgs {
-  MatView A;
+  MatView A;                    // CSR row blocks (matrix format 0)
+  RunView R;                    // diagonal runs (matrix format 1); exactly one of the two is set
   int n;                        // local rows
   State *S;
   double *partials;             // 2 x (kRedSlots + 1) x kMaxGrid, double-buffered
@@ -377,6 +396,31 @@ __device__ __forceinline__ void halo_wait(PersistCtx &c, const PersistArgs &a) {
   }
   __syncthreads();
 }
+
+// The SpMV pass of a persistent kernel, by matrix format.  FMT 0: the TMA-fed row-block ring
+// (prefetches the first blocks of the NEXT pass while the vector phases run); FMT 1: the
+// diagonal-run pass (plain coalesced loads, nothing to prefetch or drain, no shared memory).
+template <int FMT> struct MatPass;
+template <> struct MatPass<0> {
+  Ring<kPersistStages> ring;
+  __device__ __forceinline__ void init(unsigned char *smem, uint64_t *full, bool l2_stream, RunSmem *) { ring.init(smem, full, l2_stream); }
+  __device__ __forceinline__ void prefetch(const PersistArgs &a) { ring.prefetch(a.A); }
+  __device__ __forceinline__ void drain(const PersistArgs &a) { ring.drain(a.A); }
+  template <bool PER_BLOCK, class RowOp, class HaloOp>
+  __device__ __forceinline__ void pass(const PersistArgs &a, const double *x, double *red_sh, RowOp rowop, HaloOp haloop) {
+    ring.template pass<false, PER_BLOCK>(a.A, x, red_sh, rowop, haloop);
+  }
+};
+template <> struct MatPass<1> {
+  RunSmem *sseg;                // shared: descriptor staging of run_pass
+  __device__ __forceinline__ void init(unsigned char *, uint64_t *, bool, RunSmem *sseg_) { sseg = sseg_; }
+  __device__ __forceinline__ void prefetch(const PersistArgs &) {}
+  __device__ __forceinline__ void drain(const PersistArgs &) {}
+  template <bool PER_BLOCK, class RowOp, class HaloOp>
+  __device__ __forceinline__ void pass(const PersistArgs &a, const double *x, double *, RowOp rowop, HaloOp haloop) {
+    run_pass<false, kPersistRunUnroll, PER_BLOCK>(a.R, x, *sseg, rowop, haloop);
+  }
+};
 
 // ---- host side (psp_persist.cu)
 // fills the shared part of the arguments; zeroes the barrier scratch on the stream

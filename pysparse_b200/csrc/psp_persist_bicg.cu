@@ -30,10 +30,13 @@ struct BicgArgs : PersistArgs {
   const double *dinv;                                         // nullptr: identity preconditioner
 };
 
-__global__ void __launch_bounds__(kThreads, kPersistCtas)
+template <int FMT>
+__global__ void __launch_bounds__(kThreads, persist_ctas(FMT))
 k_bicgstab_persist(BicgArgs a, size_t p_slot_off, size_t phat_slot_off, size_t shat_slot_off) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) uint64_t full[kPersistStages];
+  __shared__ __align__(8) uint64_t full[FMT == 0 ? kPersistStages : 1];
+  __shared__ __align__(16) unsigned char sseg_raw[FMT == 1 ? sizeof(RunSmem) : 16];   // (format 0 stages its descriptors in the TMA ring)
+  RunSmem *sseg = reinterpret_cast<RunSmem *>(sseg_raw);
   __shared__ double red_sh[8 * (kRedSlots + 1)];
   __shared__ double tot[kRedSlots + 1];
   __shared__ State sS;
@@ -55,9 +58,9 @@ k_bicgstab_persist(BicgArgs a, size_t p_slot_off, size_t phat_slot_off, size_t s
   const bool do_push = push && c.debug < 1;
   const bool ident = (a.dinv == nullptr);
 
-  Ring<kPersistStages> ring;
-  ring.init(smem, full, a.l2_stream != 0);
-  ring.prefetch(a.A);
+  MatPass<FMT> ring;
+  ring.init(smem, full, a.l2_stream != 0, sseg);
+  ring.prefetch(a);
 
   // ---- ||b||  (bicgstab.c:203-216)
   {
@@ -80,9 +83,9 @@ k_bicgstab_persist(BicgArgs a, size_t p_slot_off, size_t phat_slot_off, size_t s
     else publish_and_pull(grid, c, a, a.p, p_slot_off);
     xin = p_cur;
   }
-  ring.template pass<false>(a.A, xin, red_sh, [&](int r, double sum) { a.r[r] = sum; },
+  ring.template pass<false>(a, xin, red_sh, [&](int r, double sum) { a.r[r] = sum; },
                             [&](int) { if (push) halo_wait(c, a); });
-  ring.prefetch(a.A);
+  ring.prefetch(a);
   grid.sync();
   // ---- r = b - r, rhat = r, |r|^2   (bicgstab.c:235-248)
   {
@@ -125,9 +128,9 @@ k_bicgstab_persist(BicgArgs a, size_t p_slot_off, size_t phat_slot_off, size_t s
     }
     {                                   // v = A phat ; rhat.v
       double acc[1] = {0.0};
-      ring.template pass<false>(a.A, x1, red_sh, [&](int r, double sum) { a.v[r] = sum; acc[0] += a.rhat[r] * sum; },
+      ring.template pass<false>(a, x1, red_sh, [&](int r, double sum) { a.v[r] = sum; acc[0] += a.rhat[r] * sum; },
                                 [&](int) { if (push) halo_wait(c, a); });
-      ring.prefetch(a.A);
+      ring.prefetch(a);
       grid_allreduce<1, false>(c, a, acc, 0.0);
       epilogue<1, false>(c, EPI_BICG_ALPHA);
     }
@@ -152,10 +155,10 @@ k_bicgstab_persist(BicgArgs a, size_t p_slot_off, size_t phat_slot_off, size_t s
     }
     {                                   // t = A shat ; s.t ; t.t
       double acc[2] = {0.0, 0.0};
-      ring.template pass<false>(a.A, x2, red_sh,
+      ring.template pass<false>(a, x2, red_sh,
                                 [&](int r, double sum) { a.t[r] = sum; acc[0] += a.s[r] * sum; acc[1] += sum * sum; },
                                 [&](int) { if (push) halo_wait(c, a); });
-      ring.prefetch(a.A);
+      ring.prefetch(a);
       grid_allreduce<2, false>(c, a, acc, 0.0);
       epilogue<2, false>(c, EPI_BICG_OMEGA);
     }
@@ -175,7 +178,7 @@ k_bicgstab_persist(BicgArgs a, size_t p_slot_off, size_t phat_slot_off, size_t s
     { double *tmp = p_cur; p_cur = p_new; p_new = tmp; }
   }
 
-  ring.drain(a.A);
+  ring.drain(a);
   if (blockIdx.x == 0 && tid == 0) {
     *a.S = sS;
     if (c.dd) {                         // 64-bit sequence numbers: add what this launch did (wrap-safe)
@@ -191,13 +194,16 @@ int bicg_persist_launch(const psp_mat *M, int n, const double *b, double *x, dou
                         double *p2, double *phat, double *v, double *s, double *shat, double *t, const double *dinv,
                         DistMat *dm) {
   Ctx &c = ctx();
-  static int resident = 0;
-  const int smem_bytes = kPersistStages * kStageBytes;
+  const int fmt = M->fmt;
+  const void *kern = fmt == 1 ? (const void *)k_bicgstab_persist<1> : (const void *)k_bicgstab_persist<0>;
+  const int smem_bytes = fmt == 1 ? 0 : kPersistStages * kStageBytes;
+  int &resident = c.occ_bicg[fmt];
   if (resident == 0) {
-    PSP_CUDA(cudaFuncSetAttribute(k_bicgstab_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    if (smem_bytes) PSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bicgstab_persist, kThreads, smem_bytes) != cudaSuccess || per_sm < 1)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem_bytes) != cudaSuccess || per_sm < 1)
       per_sm = 1;
+    if (per_sm > persist_ctas(fmt)) per_sm = persist_ctas(fmt);
     resident = per_sm * c.sms;
     if (resident > kMaxGrid) resident = kMaxGrid;
   }
@@ -213,8 +219,9 @@ int bicg_persist_launch(const psp_mat *M, int n, const double *b, double *x, dou
     shat_off = (size_t)(shat - dist().heap);
   }
   const int grid = persist_grid(M, n, resident);
+  a.R.chunk = run_chunk(M->nb, grid);
   void *args[] = {&a, &p_off, &phat_off, &shat_off};
-  PSP_CUDA(cudaLaunchCooperativeKernel((const void *)k_bicgstab_persist, dim3(grid), dim3(kThreads), args, smem_bytes, c.stream));
+  PSP_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kThreads), args, smem_bytes, c.stream));
   c.launches++;
   return PSP_OK;
 }

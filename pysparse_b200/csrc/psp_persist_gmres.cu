@@ -52,9 +52,12 @@ __device__ __forceinline__ bool gmres_exchange(cg::grid_group &grid, PersistCtx 
   return false;
 }
 
-__global__ void __launch_bounds__(kThreads, kPersistCtas) k_gmres_persist(GmresArgs a) {
+template <int FMT>
+__global__ void __launch_bounds__(kThreads, persist_ctas(FMT)) k_gmres_persist(GmresArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) uint64_t full[kPersistStages];
+  __shared__ __align__(8) uint64_t full[FMT == 0 ? kPersistStages : 1];
+  __shared__ __align__(16) unsigned char sseg_raw[FMT == 1 ? sizeof(RunSmem) : 16];   // (format 0 stages its descriptors in the TMA ring)
+  RunSmem *sseg = reinterpret_cast<RunSmem *>(sseg_raw);
   __shared__ double red_sh[8 * (kRedSlots + 1)];
   __shared__ double tot[kRedSlots + 1];
   __shared__ double gsh[kGmresMaxM];
@@ -85,9 +88,9 @@ __global__ void __launch_bounds__(kThreads, kPersistCtas) k_gmres_persist(GmresA
     });
   };
 
-  Ring<kPersistStages> ring;
-  ring.init(smem, full, a.l2_stream != 0);
-  ring.prefetch(a.A);
+  MatPass<FMT> ring;
+  ring.init(smem, full, a.l2_stream != 0, sseg);
+  ring.prefetch(a);
 
   // ---- ||b||  (gmres.c:100-108)
   {
@@ -107,11 +110,11 @@ __global__ void __launch_bounds__(kThreads, kPersistCtas) k_gmres_persist(GmresA
     {
       const bool unpack = gmres_exchange(grid, c, a, xin, push);
       if (unpack)
-        ring.template pass<false, true>(a.A, xin, red_sh, [&](int r, double sum) { a.V[r] = sum; },
+        ring.template pass<true>(a, xin, red_sh, [&](int r, double sum) { a.V[r] = sum; },
                                         [&](int b) { halo_unpack_block(c, a, xin, b); });
       else
-        ring.template pass<false>(a.A, xin, red_sh, [&](int r, double sum) { a.V[r] = sum; });
-      ring.prefetch(a.A);
+        ring.template pass<false>(a, xin, red_sh, [&](int r, double sum) { a.V[r] = sum; }, [](int) {});
+      ring.prefetch(a);
     }
     grid.sync();
     {
@@ -146,11 +149,11 @@ __global__ void __launch_bounds__(kThreads, kPersistCtas) k_gmres_persist(GmresA
         double acc = 0.0;
         const bool unpack = gmres_exchange(grid, c, a, wi, push);
         if (unpack)
-          ring.template pass<false, true>(a.A, wi, red_sh, [&](int r, double sum) { vn[r] = sum; acc += sum * a.V[r]; },
+          ring.template pass<true>(a, wi, red_sh, [&](int r, double sum) { vn[r] = sum; acc += sum * a.V[r]; },
                                           [&](int b) { halo_unpack_block(c, a, wi, b); });
         else
-          ring.template pass<false>(a.A, wi, red_sh, [&](int r, double sum) { vn[r] = sum; acc += sum * a.V[r]; });
-        ring.prefetch(a.A);
+          ring.template pass<false>(a, wi, red_sh, [&](int r, double sum) { vn[r] = sum; acc += sum * a.V[r]; }, [](int) {});
+        ring.prefetch(a);
         reduce1(acc, EPI_GMRES_H);                  // H(0,i)
       }
       for (int k = 0; k <= i; k++) {                // modified Gram-Schmidt (gmres.c:141-148)
@@ -188,7 +191,7 @@ __global__ void __launch_bounds__(kThreads, kPersistCtas) k_gmres_persist(GmresA
     }
   }
 
-  ring.drain(a.A);
+  ring.drain(a);
   if (blockIdx.x == 0 && tid == 0 && c.dd) {        // 64-bit sequence numbers: add what this launch did
     const unsigned nred = c.seq - (unsigned)c.dd->red_seq, nexch = c.pubs - (unsigned)c.dd->pubs_done;
     c.dd->red_seq += nred; c.dd->pubs_done += nexch; c.dd->pulls_done += nexch;
@@ -200,13 +203,16 @@ int gmres_persist_launch(const psp_mat *M, int n, const double *b, double *x, do
                          size_t N, int m, const double *dinv, const double *g, DistMat *dm) {
   Ctx &c = ctx();
   if (m > kGmresMaxM) { set_error("gmres_persist: restart length %d exceeds %d", m, kGmresMaxM); return PSP_ERR_ARG; }
-  static int resident = 0;
-  const int smem_bytes = kPersistStages * kStageBytes;
+  const int fmt = M->fmt;
+  const void *kern = fmt == 1 ? (const void *)k_gmres_persist<1> : (const void *)k_gmres_persist<0>;
+  const int smem_bytes = fmt == 1 ? 0 : kPersistStages * kStageBytes;
+  int &resident = c.occ_gmres[fmt];
   if (resident == 0) {
-    PSP_CUDA(cudaFuncSetAttribute(k_gmres_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    if (smem_bytes) PSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gmres_persist, kThreads, smem_bytes) != cudaSuccess || per_sm < 1)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem_bytes) != cudaSuccess || per_sm < 1)
       per_sm = 1;
+    if (per_sm > persist_ctas(fmt)) per_sm = persist_ctas(fmt);
     resident = per_sm * c.sms;
     if (resident > kMaxGrid) resident = kMaxGrid;
   }
@@ -215,8 +221,9 @@ int gmres_persist_launch(const psp_mat *M, int n, const double *b, double *x, do
   if (dm && !M->d_blk_halo) a.push = 0;             // block-local unpack needs the per-block halo ranges
   a.b = b; a.x = x; a.V = V; a.W = W; a.xs = xs; a.dinv = dinv; a.g = g; a.N = N; a.m = m;
   const int grid = persist_grid(M, n, resident);
+  a.R.chunk = run_chunk(M->nb, grid);
   void *args[] = {&a};
-  PSP_CUDA(cudaLaunchCooperativeKernel((const void *)k_gmres_persist, dim3(grid), dim3(kThreads), args, smem_bytes, c.stream));
+  PSP_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kThreads), args, smem_bytes, c.stream));
   c.launches++;
   return PSP_OK;
 }

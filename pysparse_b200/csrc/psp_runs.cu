@@ -1,0 +1,373 @@
+// psp_runs.cu -- analysis, upload and stand-alone kernel of the "diagonal run" format
+// (psp_runs.cuh has the format and the device pass).
+//
+// Replaces, for matrices whose rows line up on diagonals, the inner loops of
+// csr_matvec_kernel (pysparse/sparse/src/csr_mat.c:49-54) and sss_matvec (sss_mat.c:40-56).
+// Algorithmic traffic of the reference layouts is 12 bytes per stored entry (value + column
+// index); this format moves 8 (the value) plus 16 bytes per run.
+#include <algorithm>
+#include "psp_mat.cuh"
+#include "psp_epilogue.cuh"
+#include "psp_runs.cuh"
+
+namespace psp {
+
+// ------------------------------------------------------------------ kernel
+struct RunArgs {
+  RunView A;
+  const double *x;
+  double *y;
+  const double *w1, *w2;
+  int w2_is_y, epilogue, gate;
+  State *S;
+  double *partials;
+  unsigned *ticket;
+  void *aux;
+};
+
+template <bool DOTS>
+__global__ void __launch_bounds__(kThreads, 4) k_spmv_runs(RunArgs a) {
+  __shared__ double red_sh[8];
+  __shared__ RunSmem sseg;
+  if (DOTS) {
+    const volatile State *V = a.S;
+    if (V->done || (a.gate == 1 && V->cyc_done)) return;
+  }
+  double acc0 = 0.0, acc1 = 0.0;
+  run_pass<true, 8, false>(a.A, a.x, sseg, [&](int r, double sum) {
+    a.y[r] = sum;
+    if (DOTS) {
+      if (a.w1) acc0 += a.w1[r] * sum;
+      if (a.w2_is_y) acc1 += sum * sum;
+      else if (a.w2) acc1 += a.w2[r] * sum;
+    }
+  }, [](int) {});
+  if (DOTS) {
+    double mine[2];
+    mine[0] = block_sum(acc0, red_sh);
+    mine[1] = block_sum(acc1, red_sh);
+    double tot[2], dummy;
+    if (grid_reduce_finish<2, false>(mine, 0.0, a.partials, a.ticket, tot, &dummy, red_sh, a.S->dist)) {
+      if (threadIdx.x == 0) {
+        a.S->red[0] = tot[0];
+        a.S->red[1] = tot[1];
+        run_epilogue(a.epilogue, a.S, a.aux);
+      }
+    }
+  }
+}
+
+int runs_launch(const psp_mat *A, const double *dx, double *dy, const SpmvDots &d) {
+  Ctx &c = ctx();
+  RunArgs a;
+  a.A.val = A->d_rval; a.A.seg = reinterpret_cast<const int4 *>(A->d_rseg);
+  a.A.blk = reinterpret_cast<const int4 *>(A->d_rblk); a.A.nb = A->nb; a.A.nint = A->nb; a.A.blk_halo = nullptr;
+  a.x = dx; a.y = dy;
+  a.w1 = d.w1; a.w2 = d.w2; a.w2_is_y = d.w2_is_y; a.epilogue = d.epilogue; a.gate = d.gate; a.S = d.S;
+  a.partials = c.partials; a.ticket = c.tickets;
+  a.aux = d.S ? (void *)(d.S + 1) : nullptr;
+  // persistent grid: what is resident at once (the DOTS variant needs it for its ticket
+  // reduction buffers, the plain one simply has no tail of tiny waves)
+  int &res = c.occ_runs[d.S ? 1 : 0];
+  if (res == 0) {
+    int per_sm = 0;
+    const void *fn = d.S ? (const void *)k_spmv_runs<true> : (const void *)k_spmv_runs<false>;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    res = per_sm * c.sms;
+    if (res > kMaxGrid) res = kMaxGrid;
+  }
+  a.A.chunk = run_chunk(A->nb, res);
+  const int nch = (A->nb + a.A.chunk - 1) / a.A.chunk;
+  const int grid = nch < res ? nch : res;
+  if (d.S) k_spmv_runs<true><<<grid, kThreads, 0, c.stream>>>(a);
+  else k_spmv_runs<false><<<grid, kThreads, 0, c.stream>>>(a);
+  PSP_LAUNCH_CHECK();
+  return PSP_OK;
+}
+
+// ------------------------------------------------------------------ host analysis
+namespace {
+
+struct Seg { int key; int t0, len; int x0; int kpos; };     // key: (global) diagonal offset = sort key
+
+struct RunBuild {
+  std::vector<int> blk;        // 4 ints per block, natural order
+  std::vector<int> seg;        // 4 ints per run
+  std::vector<double> val;
+};
+
+// Runs of the rows [r0, r1) of a CSR structure.  A run continues from row t-1 to row t when
+// both rows have an entry on the same (global) diagonal and the local column advances by one.
+// entry_seg[k - ind[r0]] receives the block-local run number of entry k.
+void scan_block(const int *ind, const int *col, const int *gcol, int grow0, int r0, int r1, std::vector<Seg> &segs,
+                std::vector<int> *entry_seg) {
+  struct Open { int key, id; };
+  static thread_local std::vector<Open> prev, cur;
+  prev.clear();
+  segs.clear();
+  const int k0 = ind[r0];
+  if (entry_seg) entry_seg->resize((size_t)(ind[r1] - k0));
+  for (int r = r0; r < r1; r++) {
+    const int t = r - r0;
+    cur.clear();
+    size_t p = 0;
+    for (int k = ind[r]; k < ind[r + 1]; k++) {
+      const int key = (gcol ? gcol[k] : col[k]) - (grow0 + r);
+      while (p < prev.size() && prev[p].key < key) p++;
+      int id = -1;
+      if (p < prev.size() && prev[p].key == key) {
+        Seg &s = segs[(size_t)prev[p].id];
+        if (s.x0 + s.len == col[k]) { id = prev[p].id; s.len++; }
+      }
+      if (id < 0) {
+        id = (int)segs.size();
+        segs.push_back(Seg{key, t, 1, col[k], 0});
+      }
+      if (entry_seg) (*entry_seg)[(size_t)(k - k0)] = id;
+      cur.push_back(Open{key, id});
+    }
+    prev.swap(cur);
+  }
+}
+
+// cheap look at a sample of blocks: is the format worth a full analysis?
+bool sample_accepts(int m, const int *ind, const int *col, const int *gcol, int grow0) {
+  const int nb = (m + kThreads - 1) / kThreads;
+  if (nb == 0) return false;
+  std::vector<Seg> segs;
+  long long nseg = 0, nent = 0;
+  const int nsample = nb < 48 ? nb : 48;
+  for (int i = 0; i < nsample; i++) {
+    const int b = (int)((long long)i * nb / nsample);
+    const int r0 = b * kThreads, r1 = std::min(m, r0 + kThreads);
+    if ((long long)ind[r1] - ind[r0] > 64 * kThreads) return false;    // long rows: not this format's case
+    scan_block(ind, col, gcol, grow0, r0, r1, segs, nullptr);
+    nseg += (long long)segs.size();
+    nent += ind[r1] - ind[r0];
+  }
+  return nent > 0 && nseg * 8 <= nent;
+}
+
+int upload_raw(const void *src, size_t bytes, void **dst) {
+  void *p = nullptr;
+  const size_t pad = 64;
+  cudaError_t e = cudaMalloc(&p, bytes + pad);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("cudaMalloc(%zu bytes) failed: %s", bytes + pad, cudaGetErrorString(e));
+    return PSP_ERR_NOMEM;
+  }
+  if (cudaMemset(p, 0, bytes + pad) != cudaSuccess || (bytes && cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess)) {
+    cudaGetLastError();
+    cudaFree(p);
+    set_error("upload of %zu bytes failed", bytes);
+    return PSP_ERR_CUDA;
+  }
+  *dst = p;
+  return PSP_OK;
+}
+
+// own_cols >= 0: blocks that read no halo column first (their number -> *nint), and per
+// scheduled block the range of halo positions it reads (bh, 2 ints per block)
+int upload_runs(psp_mat *A, RunBuild &rb, int own_cols) {
+  const int nb = (int)(rb.blk.size() / 4);
+  std::vector<int> sched;
+  std::vector<int> bh;
+  int nint = nb;
+  if (own_cols >= 0) {
+    std::vector<int> interior, boundary;
+    std::vector<int> lo((size_t)nb, INT32_MAX), hi((size_t)nb, -1);
+    for (int b = 0; b < nb; b++) {
+      for (int s = rb.blk[4 * (size_t)b + 2]; s < rb.blk[4 * (size_t)b + 3]; s++) {
+        const int x0 = rb.seg[4 * (size_t)s + 1], len = rb.seg[4 * (size_t)s + 3];
+        if (x0 + len > own_cols) {
+          const int a0 = (x0 > own_cols ? x0 : own_cols) - own_cols, a1 = x0 + len - own_cols;
+          if (a0 < lo[b]) lo[b] = a0;
+          if (a1 > hi[b]) hi[b] = a1;
+        }
+      }
+      (hi[b] >= 0 ? boundary : interior).push_back(b);
+    }
+    nint = (int)interior.size();
+    sched.reserve((size_t)nb * 4);
+    bh.assign(2 * (size_t)nb, 0);
+    // the run descriptors follow the schedule: consecutive blocks of the schedule have
+    // consecutive descriptor ranges (run_pass fetches them chunk-wise)
+    std::vector<int> seg2;
+    seg2.reserve(rb.seg.size());
+    int i = 0;
+    for (const std::vector<int> *lst : {&interior, &boundary})
+      for (int b : *lst) {
+        const int s0 = rb.blk[4 * (size_t)b + 2], s1 = rb.blk[4 * (size_t)b + 3];
+        sched.push_back(rb.blk[4 * (size_t)b]); sched.push_back(rb.blk[4 * (size_t)b + 1]);
+        sched.push_back((int)(seg2.size() / 4));
+        seg2.insert(seg2.end(), rb.seg.begin() + 4 * (size_t)s0, rb.seg.begin() + 4 * (size_t)s1);
+        sched.push_back((int)(seg2.size() / 4));
+        if (hi[b] >= 0) { bh[2 * (size_t)i] = lo[b]; bh[2 * (size_t)i + 1] = hi[b]; }
+        i++;
+      }
+    rb.seg.swap(seg2);
+  }
+  const std::vector<int> &blk = own_cols >= 0 ? sched : rb.blk;
+  PSP_TRY(upload_raw(rb.val.data(), sizeof(double) * rb.val.size(), (void **)&A->d_rval));
+  PSP_TRY(upload_raw(rb.seg.data(), sizeof(int) * rb.seg.size(), (void **)&A->d_rseg));
+  PSP_TRY(upload_raw(blk.data(), sizeof(int) * blk.size(), (void **)&A->d_rblk));
+  if (own_cols >= 0) PSP_TRY(upload_raw(bh.data(), sizeof(int) * bh.size(), (void **)&A->d_blk_halo));
+  A->fmt = 1;
+  A->nb = nb; A->nint = nint;
+  A->rval_len = (long long)rb.val.size();
+  A->nseg = (int)(rb.seg.size() / 4);
+  return PSP_OK;
+}
+
+bool by_key_then_row(const Seg &a, const Seg &b) { return a.key != b.key ? a.key < b.key : a.t0 < b.t0; }
+
+}  // namespace
+
+int runs_try_csr(psp_mat *A, const int *ind, const int *col, const double *val, const int *gcol, int grow0,
+                 int own_cols, bool *accepted) {
+  *accepted = false;
+  Ctx &c = ctx();
+  const int m = A->m;
+  const long long nnz = ind[m];
+  if (c.spmv_format == 0 || m == 0 || nnz == 0) return PSP_OK;
+  if (c.spmv_format < 0 && !sample_accepts(m, ind, col, gcol, grow0)) return PSP_OK;
+  const int nb = (m + kThreads - 1) / kThreads;
+  RunBuild rb;
+  rb.blk.resize(4 * (size_t)nb);
+  rb.val.resize((size_t)nnz);
+  std::vector<Seg> segs;
+  std::vector<int> entry_seg, order;
+  long long kpos = 0;
+  for (int b = 0; b < nb; b++) {
+    const int r0 = b * kThreads, r1 = std::min(m, r0 + kThreads);
+    scan_block(ind, col, gcol, grow0, r0, r1, segs, &entry_seg);
+    order.resize(segs.size());
+    for (size_t i = 0; i < segs.size(); i++) order[i] = (int)i;
+    std::sort(order.begin(), order.end(), [&](int x, int y) { return by_key_then_row(segs[(size_t)x], segs[(size_t)y]); });
+    rb.blk[4 * (size_t)b] = r0; rb.blk[4 * (size_t)b + 1] = r1 - r0;
+    rb.blk[4 * (size_t)b + 2] = (int)(rb.seg.size() / 4);
+    for (int id : order) {
+      Seg &s = segs[(size_t)id];
+      s.kpos = (int)kpos;
+      kpos += s.len;
+      rb.seg.push_back(s.kpos); rb.seg.push_back(s.x0); rb.seg.push_back(s.t0); rb.seg.push_back(s.len);
+    }
+    rb.blk[4 * (size_t)b + 3] = (int)(rb.seg.size() / 4);
+    const int k0 = ind[r0];
+    for (int r = r0; r < r1; r++)
+      for (int k = ind[r]; k < ind[r + 1]; k++) {
+        const Seg &s = segs[(size_t)entry_seg[(size_t)(k - k0)]];
+        rb.val[(size_t)s.kpos + (size_t)(r - r0 - s.t0)] = val[k];
+      }
+    // give up early on matrices the sample misjudged
+    if (c.spmv_format < 0 && (b & 1023) == 1023 && (long long)(rb.seg.size() / 4) * 8 > (long long)ind[r1]) return PSP_OK;
+  }
+  if (c.spmv_format < 0 && (long long)(rb.seg.size() / 4) * 16 > nnz) return PSP_OK;     // mean run shorter than 16 rows
+  PSP_TRY(upload_runs(A, rb, own_cols));
+  *accepted = true;
+  return PSP_OK;
+}
+
+int runs_try_sss(psp_mat *A, const int *ind, const int *col, const double *val, const double *diag, bool *accepted) {
+  *accepted = false;
+  Ctx &c = ctx();
+  const int n = A->n;
+  const long long nnz = ind[n];
+  if (c.spmv_format == 0 || n == 0) return PSP_OK;
+  if (nnz > 0 && c.spmv_format < 0 && !sample_accepts(n, ind, col, nullptr, 0)) return PSP_OK;
+  if (nnz + n >= (1LL << 31)) return PSP_OK;
+  const int nb = (n + kThreads - 1) / kThreads;
+  RunBuild rb;
+  rb.val.resize((size_t)nnz + (size_t)n);
+  std::copy(diag, diag + n, rb.val.begin() + nnz);
+  struct Upper { int tb; Seg s; };
+  std::vector<std::vector<Seg>> lower((size_t)nb);
+  std::vector<Upper> upper;
+  std::vector<Seg> segs;
+  std::vector<int> entry_seg;
+  long long kpos = 0;
+  for (int b = 0; b < nb; b++) {
+    const int r0 = b * kThreads, r1 = std::min(n, r0 + kThreads);
+    scan_block(ind, col, nullptr, 0, r0, r1, segs, &entry_seg);
+    std::vector<int> order(segs.size());
+    for (size_t i = 0; i < segs.size(); i++) order[i] = (int)i;
+    std::sort(order.begin(), order.end(), [&](int x, int y) { return by_key_then_row(segs[(size_t)x], segs[(size_t)y]); });
+    for (int id : order) {
+      Seg &s = segs[(size_t)id];
+      s.kpos = (int)kpos;
+      kpos += s.len;
+      lower[(size_t)b].push_back(s);
+      // the mirrored use of the same values: entry (i, j) adds val * x[i] to y[j]; rows
+      // i0 .. i0+len-1 of this run are the columns of target rows j0 .. j0+len-1, j0 = i0 + key
+      int i0 = r0 + s.t0, j0 = i0 + s.key, left = s.len, kp = s.kpos;
+      while (left > 0) {
+        const int tb = j0 / kThreads, tt = j0 % kThreads;
+        const int piece = std::min(left, kThreads - tt);
+        upper.push_back(Upper{tb, Seg{-s.key, tt, piece, i0, kp}});
+        i0 += piece; j0 += piece; kp += piece; left -= piece;
+      }
+    }
+    const int k0 = ind[r0];
+    for (int r = r0; r < r1; r++)
+      for (int k = ind[r]; k < ind[r + 1]; k++) {
+        const Seg &s = segs[(size_t)entry_seg[(size_t)(k - k0)]];
+        rb.val[(size_t)s.kpos + (size_t)(r - r0 - s.t0)] = val[k];
+      }
+  }
+  long long nseg = (long long)upper.size() * 2 + nb;
+  if (c.spmv_format < 0 && nnz > 0 && nseg * 16 > 2 * nnz + n) return PSP_OK;
+  // counting sort of the mirrored runs by target block, then by (diagonal, row) inside a block
+  std::vector<int> start((size_t)nb + 1, 0);
+  for (const Upper &u : upper) start[(size_t)u.tb + 1]++;
+  for (int b = 0; b < nb; b++) start[(size_t)b + 1] += start[(size_t)b];
+  std::vector<Seg> usorted(upper.size());
+  {
+    std::vector<int> fill(start.begin(), start.end() - 1);
+    for (const Upper &u : upper) usorted[(size_t)fill[(size_t)u.tb]++] = u.s;
+  }
+  rb.blk.resize(4 * (size_t)nb);
+  for (int b = 0; b < nb; b++) {
+    const int r0 = b * kThreads, r1 = std::min(n, r0 + kThreads);
+    std::sort(usorted.begin() + start[(size_t)b], usorted.begin() + start[(size_t)b + 1], by_key_then_row);
+    rb.blk[4 * (size_t)b] = r0; rb.blk[4 * (size_t)b + 1] = r1 - r0;
+    rb.blk[4 * (size_t)b + 2] = (int)(rb.seg.size() / 4);
+    auto emit = [&](const Seg &s) { rb.seg.push_back(s.kpos); rb.seg.push_back(s.x0); rb.seg.push_back(s.t0); rb.seg.push_back(s.len); };
+    for (const Seg &s : lower[(size_t)b]) emit(s);
+    emit(Seg{0, 0, r1 - r0, r0, (int)(nnz + r0)});                    // the diagonal
+    for (int i = start[(size_t)b]; i < start[(size_t)b + 1]; i++) emit(usorted[(size_t)i]);
+    rb.blk[4 * (size_t)b + 3] = (int)(rb.seg.size() / 4);
+  }
+  PSP_TRY(upload_runs(A, rb, -1));
+  A->d_diag = A->d_rval + nnz;          // the SSOR sweeps read the diagonal from here
+  *accepted = true;
+  return PSP_OK;
+}
+
+int runs_to_csr(const psp_mat *A, std::vector<int> &ind, std::vector<int> &col, std::vector<double> &val) {
+  if (A->fmt != 1 || A->kind != 1) { set_error("runs_to_csr: not a CSR matrix in run format"); return PSP_ERR_ARG; }
+  std::vector<int> blk(4 * (size_t)A->nb), seg(4 * (size_t)A->nseg);
+  std::vector<double> rv((size_t)A->rval_len);
+  PSP_CUDA(cudaMemcpy(blk.data(), A->d_rblk, sizeof(int) * blk.size(), cudaMemcpyDeviceToHost));
+  PSP_CUDA(cudaMemcpy(seg.data(), A->d_rseg, sizeof(int) * seg.size(), cudaMemcpyDeviceToHost));
+  PSP_CUDA(cudaMemcpy(rv.data(), A->d_rval, sizeof(double) * rv.size(), cudaMemcpyDeviceToHost));
+  const int m = A->m;
+  ind.assign((size_t)m + 1, 0);
+  for (int b = 0; b < A->nb; b++)
+    for (int s = blk[4 * (size_t)b + 2]; s < blk[4 * (size_t)b + 3]; s++)
+      for (int u = 0; u < seg[4 * (size_t)s + 3]; u++) ind[(size_t)(blk[4 * (size_t)b] + seg[4 * (size_t)s + 2] + u) + 1]++;
+  for (int r = 0; r < m; r++) ind[(size_t)r + 1] += ind[(size_t)r];
+  col.resize((size_t)ind[(size_t)m]); val.resize((size_t)ind[(size_t)m]);
+  std::vector<int> fill(ind.begin(), ind.end() - 1);
+  for (int b = 0; b < A->nb; b++)                   // runs of a block are in ascending-column order per row
+    for (int s = blk[4 * (size_t)b + 2]; s < blk[4 * (size_t)b + 3]; s++)
+      for (int u = 0; u < seg[4 * (size_t)s + 3]; u++) {
+        const int r = blk[4 * (size_t)b] + seg[4 * (size_t)s + 2] + u;
+        const int p = fill[(size_t)r]++;
+        col[(size_t)p] = seg[4 * (size_t)s + 1] + u;
+        val[(size_t)p] = rv[(size_t)seg[4 * (size_t)s] + (size_t)u];
+      }
+  return PSP_OK;
+}
+
+}  // namespace psp

@@ -253,6 +253,7 @@ extern "C" int psp_set_option(const char *name, long long value) {
   Ctx &c = g_ctx;
   if (!strcmp(name, "spmv_variant")) c.spmv_variant = value;
   else if (!strcmp(name, "spmv_ctas")) c.spmv_ctas = value;
+  else if (!strcmp(name, "spmv_format")) c.spmv_format = value;
   else if (!strcmp(name, "poll_chunk")) c.poll_chunk = value;
   else if (!strcmp(name, "l2_stream")) c.l2_stream = value;
   else if (!strcmp(name, "pcg_persist")) c.pcg_persist = value;
@@ -271,6 +272,7 @@ extern "C" long long psp_get_option(const char *name) {
   if (!name) return -1;
   if (!strcmp(name, "spmv_variant")) return c.spmv_variant;
   if (!strcmp(name, "spmv_ctas")) return c.spmv_ctas;
+  if (!strcmp(name, "spmv_format")) return c.spmv_format;
   if (!strcmp(name, "poll_chunk")) return c.poll_chunk;
   if (!strcmp(name, "sms")) return c.sms;
   if (!strcmp(name, "l2_stream")) return c.l2_stream;

@@ -334,12 +334,15 @@ static int finish_csr_upload(psp_mat *A, const std::vector<int> &ind, const int 
 }
 
 int csr_create(int m, int n, long long nnz, const int *ind, const int *col, const double *val,
-               psp_mat **out, bool keep_host, int own_cols) {
+               psp_mat **out, bool keep_host, int own_cols, const int *gcol, int grow0) {
   PSP_TRY(check_csr(m, n, nnz, ind, col, false));
   psp_mat *A = new psp_mat();
   A->kind = 1; A->m = m; A->n = n; A->nnz = nnz; A->fnnz = nnz;
   std::vector<int> hind(ind, ind + m + 1);
-  int st = finish_csr_upload(A, hind, col, val, own_cols);
+  // rows lined up on diagonals: the run format (no column indices on the device at all)
+  bool runs = false;
+  int st = runs_try_csr(A, ind, col, val, gcol, grow0, own_cols, &runs);
+  if (st == PSP_OK && !runs) st = finish_csr_upload(A, hind, col, val, own_cols);
   if (st != PSP_OK) { psp_mat_destroy(A); return st; }
   if (keep_host) {
     A->h_ind.swap(hind);
@@ -354,9 +357,25 @@ int sss_create(int n, long long nnz, const int *ind, const int *col, const doubl
                const double *diag, psp_mat **out) {
   PSP_TRY(check_csr(n, n, nnz, ind, col, true));
   long long fnnz = 2 * nnz + n;
-  if (fnnz >= (1LL << 31)) { set_error("expanded SSS matrix exceeds 2^31 entries"); return PSP_ERR_ARG; }
   psp_mat *A = new psp_mat();
   A->kind = 2; A->m = n; A->n = n; A->nnz = nnz; A->fnnz = fnnz;
+  {
+    // SSS-native: every stored entry of the lower triangle is kept ONCE on the device and used
+    // for both products of sss_matvec (sss_mat.c:47-54) through two run descriptors
+    bool runs = false;
+    int st = runs_try_sss(A, ind, col, val, diag, &runs);
+    if (st != PSP_OK) { psp_mat_destroy(A); return st; }
+    if (runs) {
+      A->h_ind.assign(ind, ind + n + 1);
+      A->h_col.assign(col, col + nnz);
+      A->h_val.assign(val, val + nnz);
+      A->h_diag.assign(diag, diag + n);
+      *out = A;
+      return PSP_OK;
+    }
+  }
+  // irregular symmetric matrices: fall back to the one-time symmetric expansion
+  if (fnnz >= (1LL << 31)) { psp_mat_destroy(A); set_error("expanded SSS matrix exceeds 2^31 entries"); return PSP_ERR_ARG; }
   // symmetric expansion in to_csr() order (ll_mat.c:1601-1623)
   std::vector<int> find((size_t)n + 1, 0), fcol((size_t)fnnz), fill((size_t)n);
   std::vector<double> fval((size_t)fnnz);
@@ -375,9 +394,6 @@ int sss_create(int n, long long nnz, const int *ind, const int *col, const doubl
       fcol[fill[j]] = i; fval[fill[j]] = val[k]; fill[j]++;
     }
   int st = finish_csr_upload(A, find, fcol.data(), fval.data());
-  if (st == PSP_OK) st = upload(ind, sizeof(int) * (size_t)(n + 1), (void **)&A->d_lind);
-  if (st == PSP_OK) st = upload(col, sizeof(int) * (size_t)nnz, (void **)&A->d_lcol);
-  if (st == PSP_OK) st = upload(val, sizeof(double) * (size_t)nnz, (void **)&A->d_lval);
   if (st == PSP_OK) st = upload(diag, sizeof(double) * (size_t)n, (void **)&A->d_diag);
   if (st == PSP_OK && cudaStreamSynchronize(ctx().stream) != cudaSuccess) st = PSP_ERR_CUDA;
   if (st != PSP_OK) { psp_mat_destroy(A); return st; }
@@ -401,6 +417,7 @@ int mat_transpose(psp_mat *A) {
   std::vector<int> ind, col;
   std::vector<double> val;
   if (!A->h_ind.empty()) { ind = A->h_ind; col = A->h_col; val = A->h_val; }
+  else if (A->fmt == 1) { PSP_TRY(runs_to_csr(A, ind, col, val)); }
   else {
     ind.resize((size_t)m + 1); col.resize((size_t)nnz); val.resize((size_t)nnz);
     PSP_CUDA(cudaMemcpy(ind.data(), A->d_ind, sizeof(int) * (size_t)(m + 1), cudaMemcpyDeviceToHost));
@@ -418,7 +435,7 @@ int mat_transpose(psp_mat *A) {
       tcol[fill[j]] = i; tval[fill[j]] = val[k]; fill[j]++;
     }
   psp_mat *T = nullptr;
-  PSP_TRY(csr_create(n, m, nnz, tind.data(), tcol.data(), tval.data(), &T, false, -1));
+  PSP_TRY(csr_create(n, m, nnz, tind.data(), tcol.data(), tval.data(), &T, false, -1, nullptr, 0));
   A->transp = T;
   return PSP_OK;
 }
@@ -449,6 +466,7 @@ int spmv_launch(const psp_mat *A, const double *dx, double *dy, const SpmvDots &
 
 static int spmv_dispatch(const psp_mat *A, const double *dx, double *dy, const SpmvDots &d) {
   Ctx &c = ctx();
+  if (A->fmt == 1) return runs_launch(A, dx, dy, d);
   SpmvArgs a;
   a.ind = A->d_ind; a.col = A->d_col; a.blk = A->d_blk; a.val = A->d_val;
   a.x = dx; a.y = dy; a.nb = A->nb;
@@ -494,7 +512,7 @@ static int spmv_dispatch(const psp_mat *A, const double *dx, double *dy, const S
 using namespace psp;
 
 namespace psp {
-int csr_create(int, int, long long, const int *, const int *, const double *, psp_mat **, bool, int);
+int csr_create(int, int, long long, const int *, const int *, const double *, psp_mat **, bool, int, const int *, int);
 int sss_create(int, long long, const int *, const int *, const double *, const double *, psp_mat **);
 }
 
@@ -502,7 +520,7 @@ extern "C" int psp_csr_create(int m, int n, int nnz, const int *ind, const int *
                               const double *val, psp_mat **out) {
   if (!out || !ind || (nnz > 0 && (!col || !val))) { set_error("psp_csr_create: NULL argument"); return PSP_ERR_ARG; }
   PSP_TRY(ensure_init());
-  return csr_create(m, n, nnz, ind, col, val, out, false, -1);
+  return csr_create(m, n, nnz, ind, col, val, out, false, -1, nullptr, 0);
 }
 
 extern "C" int psp_sss_create(int n, int nnz, const int *ind, const int *col, const double *val,
@@ -519,7 +537,8 @@ extern "C" void psp_mat_destroy(psp_mat *A) {
   if (!A) return;
   if (A->transp) psp_mat_destroy(A->transp);
   cudaFree(A->d_ind); cudaFree(A->d_col); cudaFree(A->d_val); cudaFree(A->d_blk); cudaFree(A->d_blk_halo);
-  cudaFree(A->d_lind); cudaFree(A->d_lcol); cudaFree(A->d_lval); cudaFree(A->d_diag);
+  if (!(A->fmt == 1 && A->kind == 2)) cudaFree(A->d_diag);      // run format: the diagonal lives inside d_rval
+  cudaFree(A->d_rval); cudaFree(A->d_rseg); cudaFree(A->d_rblk);
   cudaFree(A->d_x); cudaFree(A->d_y);
   delete A;
 }

@@ -70,11 +70,14 @@ def test_hot_kernels_keep_their_register_budget(native):
         m = re.search(r"REG:(\d+) STACK:(\d+)", line)
         if m and name:
             usage[name] = (int(m.group(1)), int(m.group(2)))
-    persist = [v for k, v in usage.items() if "k_pcg_persist" in k]
-    assert persist, "k_pcg_persist not found in the library"
-    for reg, stack in persist:
-        assert reg <= 64 and stack <= 32, (reg, stack)
-    spmv = [v for k, v in usage.items() if "k_spmv_tma" in k]
-    assert len(spmv) >= 2
+    persist = {k: v for k, v in usage.items() if "k_pcg_persist" in k}
+    assert len(persist) == 2, "k_pcg_persist<0> / <1> not found in the library"
+    for k, (reg, stack) in persist.items():
+        if "ILi1E" in k:      # diagonal-run format: loads kept in flight from registers, no spills at all
+            assert reg <= 64 and stack == 0, (k, reg, stack)
+        else:                 # CSR row blocks through the TMA ring
+            assert reg <= 64 and stack <= 32, (k, reg, stack)
+    spmv = [v for k, v in usage.items() if "k_spmv_tma" in k or "k_spmv_runs" in k]
+    assert len(spmv) >= 4
     for reg, stack in spmv:
         assert reg <= 64 and stack == 0, (reg, stack)

@@ -28,10 +28,14 @@ def gpu(native):
     return GpuLib(native)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, "runs", "auto"])
 @pytest.mark.parametrize("kc", KERNEL_CASES, ids=lambda c: c["id"])
 def test_spmv_and_precon_kernels_vs_golden(gpu, native, kc, variant):
-    native.set_option("spmv_variant", variant)
+    """variant 1-4: the CSR row-block kernels (register-streamed / TMA ring, device format 0);
+    "runs": the diagonal-run format forced on every matrix, irregular ones included (their blocks
+    overflow the descriptor cache: slow path); "auto": what the analysis picks."""
+    native.set_option("spmv_variant", variant if isinstance(variant, int) else 0)
+    native.set_option("spmv_format", 0 if isinstance(variant, int) else (1 if variant == "runs" else -1))
     try:
         G = load_kernels()
         mat = build_matrix(kc["matrix"])
@@ -63,6 +67,7 @@ def test_spmv_and_precon_kernels_vs_golden(gpu, native, kc, variant):
                 assert relmax(z, G[f"{key}/jacobi_{om}_{st}"]) <= SPMV_TOL
     finally:
         native.set_option("spmv_variant", 0)
+        native.set_option("spmv_format", -1)
 
 
 def test_spmv_strided_views(gpu, checker):
@@ -78,8 +83,17 @@ def test_spmv_strided_views(gpu, checker):
     assert np.array_equal(ys, yo)
 
 
+@pytest.fixture(params=["auto", "rowblocks"])
+def device_format(request, native):
+    """Both device layouts of a matrix: what the analysis picks (diagonal runs for every stencil
+    matrix of the suite) and the CSR row-block stream forced."""
+    native.set_option("spmv_format", -1 if request.param == "auto" else 0)
+    yield request.param
+    native.set_option("spmv_format", -1)
+
+
 @pytest.mark.parametrize("case", SOLVER_CASES, ids=lambda c: c["id"])
-def test_solvers_vs_golden_and_oracle(gpu, checker, case):
+def test_solvers_vs_golden_and_oracle(gpu, checker, case, device_format):
     mat = build_matrix(case["matrix"])
     n = mat["n"]
     A, K = make_ops(gpu, mat, case)
@@ -210,7 +224,7 @@ PCG_CASES = [c for c in SOLVER_CASES if c["solver"] == "pcg"]
 
 
 @pytest.mark.parametrize("case", PCG_CASES, ids=lambda c: c["id"])
-def test_pcg_single_launch_kernel_vs_per_phase_kernels(gpu, native, case):
+def test_pcg_single_launch_kernel_vs_per_phase_kernels(gpu, native, case, device_format):
     """The persistent single-launch PCG kernel (default) and the per-phase kernel sequence
     are two schedules of the same algorithm: same flag, same iteration count, same
     residual to rounding, on every PCG case of the suite (zero rhs, maxit hit, long rows,
@@ -236,6 +250,33 @@ def test_pcg_single_launch_kernel_vs_per_phase_kernels(gpu, native, case):
         assert abs(r0[2] - r1[2]) <= max(RELRES_TOL, 1e-6 * abs(r0[2])), (r0, r1)
     scale = max(1.0, float(np.max(np.abs(x0))))
     assert float(np.max(np.abs(x0 - x1))) <= 50 * case["tol"] * scale * max(1.0, n ** 0.5) + 1e-9 * scale
+
+
+BICG_CASES = [c for c in SOLVER_CASES if c["solver"] == "bicgstab" and c.get("prec") in (None, "jacobi") and c.get("steps", 1) == 1]
+
+
+@pytest.mark.parametrize("case", BICG_CASES, ids=lambda c: c["id"])
+def test_bicgstab_single_launch_kernel_vs_per_phase_kernels(gpu, native, case, device_format):
+    """k_bicgstab_persist (option bicg_persist = 1; the per-phase sequence stays the single-GPU
+    default because it is faster there, profiles/r2_persist_notes.md) runs the same arithmetic
+    in the same order as the per-phase kernels: identical flag, count, residual and iterate."""
+    mat = build_matrix(case["matrix"])
+    n = mat["n"]
+    out = []
+    for persist in (0, 1):
+        native.set_option("bicg_persist", persist)
+        try:
+            A, K = make_ops(gpu, mat, case)
+            b, x = start_vectors(case, n)
+            native.launch_count(reset=True)
+            r = gpu.solve("bicgstab", A, b, x, case["tol"], case["maxit"], K)
+            out.append((r, x.copy(), native.launch_count()))
+        finally:
+            native.set_option("bicg_persist", 0)
+    (r0, x0, l0), (r1, x1, l1) = out
+    assert l1 == 1 and l0 > 1
+    assert r0[:2] == r1[:2] and (r0[2] == r1[2] or (np.isnan(r0[2]) and np.isnan(r1[2]))), (r0, r1)
+    assert np.array_equal(x0, x1)
 
 
 @pytest.mark.parametrize("matrix", [["poisson2d", 40], ["random_sym", 3000, 7, 4], ["poisson3d", 12]],
