@@ -133,7 +133,7 @@ struct Ctx {
   long long spmv_ctas = 0;    // cap on resident CTAs per SM for the TMA SpMV (0: occupancy limit)
   long long l2_stream = -1;   // L2 evict-first hint on the matrix stream: 1 on, 0 off, -1 automatic
   long long pcg_persist = -1; // single-launch PCG: 1 always, 0 never, -1 automatic
-  long long ssor_engine = 0;  // SSOR sweeps: 0 automatic, 1 grid-wide barrier, 2 cluster barrier
+  long long ssor_engine = 0;  // SSOR sweeps: 0 automatic, 1 grid-wide barrier, 2 cluster barrier, 3 single CTA, 4 point-to-point (read when the preconditioner is created)
   long long ssor_cluster = 8; // CTAs in the sweep cluster (8 portable, 16 non-portable)
   long long gmres_persist = 0; // 1: single-launch GMRES kernel (psp_persist_gmres.cu; not yet validated on a GPU)
   long long bicg_persist = 0; // 1: single-launch BiCGSTAB kernel (psp_persist_bicg.cu; not yet validated on a GPU)

@@ -62,6 +62,16 @@ struct psp_prec {
   int maxw_f = 0, maxw_b = 0;                     // widest level of each schedule
   std::vector<int> h_level_f, h_level_b;
   unsigned *d_bar = nullptr;                      // grid barrier counter
+  // point-to-point ("wavefront strip") sweep engine, psp_sweep_p2p.cuh: per direction the chain
+  // schedule in warp-slot-lane order; p2p_ok == false: not applicable to this matrix
+  struct P2PSched {
+    int nwarps = 0, D = 0;
+    long long nslots = 0;
+    int *d_wbase = nullptr;
+    void *d_rec = nullptr;        // packed records (row, diagonal, dependencies) per (slot, lane)
+  } p2p[2];                                        // [0] forward, [1] backward
+  bool p2p_ok = false;
+  int *d_abort = nullptr;
   double *d_x = nullptr, *d_y = nullptr;
 };
 

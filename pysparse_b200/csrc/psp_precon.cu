@@ -24,6 +24,7 @@
 #include <cooperative_groups.h>
 #include "psp_mat.cuh"
 #include "psp_vec.cuh"
+#include "psp_sweep_p2p.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -358,6 +359,135 @@ static int grid_engine_blocks(const void *kernel) {
   return *slot;
 }
 
+static int upload_i(const std::vector<int> &v, int **d);
+static int upload_d(const std::vector<double> &v, double **d);
+
+// ---------------------------------------------------------------- point-to-point engine (host side)
+__global__ void k_fill_bits(unsigned long long *p, size_t n, unsigned long long v, const State *S) {
+  if (S && *(const volatile int *)&S->done) return;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
+}
+
+template <bool RELAX>
+static const void *p2p_kernel(int D) {
+  if (D <= 2) return (const void *)k_sweep_p2p<RELAX, 2>;
+  if (D <= 4) return (const void *)k_sweep_p2p<RELAX, 4>;
+  return (const void *)k_sweep_p2p<RELAX, 8>;
+}
+static int p2p_width(int D) { return D <= 2 ? 2 : (D <= 4 ? 4 : 8); }
+static size_t p2p_smem(int D) { return D <= 2 ? p2p_smem_bytes<2>() : (D <= 4 ? p2p_smem_bytes<4>() : p2p_smem_bytes<8>()); }
+
+// One application: 2 * steps half sweeps, each one cooperative launch of nwarps single-warp
+// CTAs.  The half sweeps ping-pong between a scratch vector and dy (forward -> scratch,
+// backward -> dy), each target pre-filled with the sentinel.
+static int p2p_apply(psp_prec *K, const double *dx, double *dy, State *gateS, bool relax) {
+  Ctx &c = ctx();
+  const size_t n = (size_t)K->n;
+  if (!K->d_t2) {
+    if (cudaMalloc((void **)&K->d_t2, sizeof(double) * n) != cudaSuccess) { cudaGetLastError(); set_error("ssor: out of device memory"); return PSP_ERR_NOMEM; }
+  }
+  PSP_CUDA(cudaMemsetAsync(K->d_abort, 0, sizeof(int), c.stream));
+  for (int step = 0; step < K->steps; step++)
+    for (int half = 0; half < 2; half++) {
+      const psp_prec::P2PSched &sc = K->p2p[half];
+      double *xnew = half == 0 ? K->d_t2 : dy;
+      const double *xold = half == 0 ? dy : K->d_t2;
+      k_fill_bits<<<grid_for(n), kThreads, 0, c.stream>>>(reinterpret_cast<unsigned long long *>(xnew), n, kSweepSentinel, gateS);
+      PSP_LAUNCH_CHECK();
+      P2PArgs a;
+      a.dir.wbase = sc.d_wbase; a.dir.rec = sc.d_rec;
+      a.dir.nwarps = sc.nwarps; a.dir.D = p2p_width(sc.D);
+      a.b = dx; a.xold = xold; a.xnew = xnew; a.w = K->d_t1; a.omega = K->omega;
+      a.first = (step == 0 && half == 0) ? 1 : 0;
+      a.reverse = half; a.n = K->n;
+      a.abort_flag = K->d_abort; a.S = gateS;
+      const void *kern = relax ? p2p_kernel<true>(sc.D) : p2p_kernel<false>(sc.D);
+      void *args[] = {&a};
+      PSP_CUDA(cudaLaunchCooperativeKernel(kern, dim3(sc.nwarps), dim3(64), args, p2p_smem(sc.D), c.stream));
+      c.launches++;
+    }
+  return PSP_OK;
+}
+
+// Chain schedule of one sweep direction.  ind/col/val: the rows of the dependency matrix (L
+// for the forward sweep; L^T with every row's entries by descending original row for the
+// backward sweep); reverse: rows are swept n-1 .. 0.  Returns false when the matrix does not
+// suit the engine (long rows, too many warps to be co-resident, too much padding).
+static bool p2p_build(int n, const std::vector<int> &ind, const std::vector<int> &col, const std::vector<double> &val,
+                      const double *diag, bool reverse, int max_warps, psp_prec::P2PSched &out, int *status) {
+  *status = PSP_OK;
+  if (n == 0) return false;
+  int D = 0;
+  for (int i = 0; i < n; i++) D = std::max(D, ind[i + 1] - ind[i]);
+  if (D > kP2PMaxDeps) return false;
+  if (D == 0) D = 1;
+  const int W = p2p_width(D);
+  // chains: a row continues the chain of its NEAREST not yet continued dependency (entries are
+  // stored farthest-back first, so the row's entries are tried last to first: on a
+  // lexicographic grid the nearest one is the previous point of the same grid line, a chain is
+  // a grid line, all chains have the same length and consecutive chains are neighbouring lines)
+  std::vector<int> chain((size_t)n, -1), pos((size_t)n, 0);
+  std::vector<char> claimed((size_t)n, 0);
+  std::vector<int> len;
+  for (int p = 0; p < n; p++) {
+    const int r = reverse ? n - 1 - p : p;
+    int parent = -1;
+    for (int k = ind[r + 1] - 1; k >= ind[r]; k--)
+      if (!claimed[(size_t)col[k]]) { parent = col[k]; break; }
+    if (parent >= 0) {
+      claimed[(size_t)parent] = 1;
+      chain[(size_t)r] = chain[(size_t)parent]; pos[(size_t)r] = pos[(size_t)parent] + 1;
+      len[(size_t)chain[(size_t)r]] = pos[(size_t)r] + 1;
+    } else {
+      chain[(size_t)r] = (int)len.size(); pos[(size_t)r] = 0;
+      len.push_back(1);
+    }
+  }
+  const int nchains = (int)len.size();
+  const int nwarps = (nchains + 31) / 32;
+  if (nwarps > max_warps) return false;
+  std::vector<int> wbase((size_t)nwarps + 1, 0);
+  for (int w = 0; w < nwarps; w++) {
+    int lmax = 0;
+    for (int cidx = 32 * w; cidx < std::min(nchains, 32 * w + 32); cidx++) lmax = std::max(lmax, len[(size_t)cidx]);
+    wbase[(size_t)w + 1] = wbase[(size_t)w] + lmax;
+  }
+  const long long nslots = wbase[(size_t)nwarps];
+  if (nslots * 32 > 3LL * n + 4096) return false;          // mostly padding: chains too uneven
+  // packed records: (row, pad, diag, W x (dep row, producing lane), W x value) per (slot, lane)
+  const size_t rb = 16 + 16 * (size_t)W;
+  std::vector<unsigned char> rec((size_t)nslots * 32 * rb, 0);
+  auto rec_at = [&](size_t slot, int lane) { return rec.data() + (slot * 32 + (size_t)lane) * rb; };
+  for (size_t e = 0; e < (size_t)nslots * 32; e++) {
+    unsigned char *p = rec.data() + e * rb;
+    const int minus1 = -1; const double one = 1.0;
+    memcpy(p, &minus1, 4); memcpy(p + 8, &one, 8);
+    for (int d = 0; d < W; d++) { memcpy(p + 16 + 8 * d, &minus1, 4); memcpy(p + 16 + 8 * d + 4, &minus1, 4); }
+  }
+  for (int r = 0; r < n; r++) {
+    const int cidx = chain[(size_t)r], w = cidx / 32, lane = cidx % 32;
+    unsigned char *p = rec_at((size_t)wbase[(size_t)w] + (size_t)pos[(size_t)r], lane);
+    memcpy(p, &r, 4); memcpy(p + 8, &diag[r], 8);
+    int d = 0;
+    for (int k = ind[r]; k < ind[r + 1]; k++, d++) {
+      const int dc = chain[(size_t)col[k]];
+      // producer inside this warp: (its position in its chain << 5) | its lane
+      const int srcl = (dc / 32 == w) ? ((pos[(size_t)col[k]] << 5) | (dc % 32)) : -1;
+      memcpy(p + 16 + 8 * d, &col[k], 4); memcpy(p + 16 + 8 * d + 4, &srcl, 4);
+      memcpy(p + 16 + 8 * (size_t)W + 8 * d, &val[k], 8);
+    }
+  }
+  out.nwarps = nwarps; out.D = D; out.nslots = nslots;
+  int st = upload_i(wbase, &out.d_wbase);
+  if (st == PSP_OK) {
+    if (cudaMalloc(&out.d_rec, rec.size() + 64) != cudaSuccess) { cudaGetLastError(); set_error("ssor: out of device memory"); st = PSP_ERR_NOMEM; }
+    else if (cudaMemcpy(out.d_rec, rec.data(), rec.size(), cudaMemcpyHostToDevice) != cudaSuccess) { cudaGetLastError(); set_error("ssor: upload failed"); st = PSP_ERR_CUDA; }
+  }
+  *status = st;
+  return st == PSP_OK;
+}
+
 int prec_apply_dev(psp_prec *K, const double *dx, double *dy, State *gateS) {
   Ctx &c = ctx();
   const long n = K->n;
@@ -381,6 +511,9 @@ int prec_apply_dev(psp_prec *K, const double *dx, double *dy, State *gateS) {
   a.nlev_b = K->nlev_b;
   a.b = dx; a.x = dy; a.w = K->d_t1; a.omega = K->omega; a.steps = K->steps; a.S = gateS;
   const bool relax = (K->omega != 1.0);
+  // point-to-point engine: long chains of narrow levels (ssor_engine 0 automatic, 4 forced)
+  if (K->p2p_ok && (c.ssor_engine == 4 || (c.ssor_engine == 0 && (long)K->nlev_f + K->nlev_b >= 64)))
+    return p2p_apply(K, dx, dy, gateS, relax);
   // engine choice: many narrow levels -> one cluster with the hardware barrier; few wide
   // levels -> the whole GPU with grid.sync.  ssor_engine: 0 auto, 1 grid, 2 cluster.
   const int maxw = K->maxw_f > K->maxw_b ? K->maxw_f : K->maxw_b;
@@ -543,6 +676,33 @@ int ssor_create(psp_mat *A, double omega, int steps, psp_prec **out) {
   if (st == PSP_OK && cudaMalloc((void **)&K->d_t1, sizeof(double) * (size_t)(n > 0 ? n : 1)) != cudaSuccess) {
     cudaGetLastError(); st = PSP_ERR_NOMEM;
   }
+  if (st == PSP_OK && ctx().ssor_engine != 1 && ctx().ssor_engine != 2 && ctx().ssor_engine != 3) {
+    // point-to-point engine: chain schedules of both sweeps, if the matrix suits it and all
+    // warps can be co-resident
+    int D = 0;
+    for (int i = 0; i < n; i++) D = std::max(D, ind[i + 1] - ind[i]);
+    for (int j = 0; j < n; j++) D = std::max(D, tind[j + 1] - tind[j]);
+    if (n > 0 && D <= kP2PMaxDeps) {
+      int per_sm = 0;
+      const void *k0 = p2p_kernel<false>(D), *k1 = p2p_kernel<true>(D);
+      int a0 = 0, a1 = 0;
+      const size_t smem = p2p_smem(D);
+      if (cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
+          cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a0, k0, 64, smem) == cudaSuccess &&
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a1, k1, 64, smem) == cudaSuccess)
+        per_sm = std::min(a0, a1);
+      else cudaGetLastError();
+      const int max_warps = per_sm * ctx().sms;
+      int s1 = PSP_OK, s2 = PSP_OK;
+      const bool ok = max_warps > 0 &&
+                      p2p_build(n, ind, col, val, A->h_diag.data(), false, max_warps, K->p2p[0], &s1) &&
+                      p2p_build(n, tind, tcol, tval, A->h_diag.data(), true, max_warps, K->p2p[1], &s2);
+      if (s1 != PSP_OK || s2 != PSP_OK) st = (s1 != PSP_OK ? s1 : s2);
+      K->p2p_ok = ok && st == PSP_OK;
+      if (K->p2p_ok && cudaMalloc((void **)&K->d_abort, sizeof(int)) != cudaSuccess) { cudaGetLastError(); st = PSP_ERR_NOMEM; }
+    }
+  }
   if (st != PSP_OK) { psp_prec_destroy(K); if (st == PSP_ERR_NOMEM) set_error("ssor: out of device memory"); return st; }
   *out = K;
   return PSP_OK;
@@ -603,7 +763,10 @@ extern "C" void psp_prec_destroy(psp_prec *K) {
   cudaFree(K->d_rows_f); cudaFree(K->d_lptr_f); cudaFree(K->d_rows_b); cudaFree(K->d_lptr_b);
   cudaFree(K->d_find); cudaFree(K->d_fcol); cudaFree(K->d_fval);
   cudaFree(K->d_bind); cudaFree(K->d_bcol); cudaFree(K->d_bval); cudaFree(K->d_floc); cudaFree(K->d_bloc);
-  cudaFree(K->d_x); cudaFree(K->d_y); cudaFree(K->d_bar);
+  cudaFree(K->d_x); cudaFree(K->d_y); cudaFree(K->d_bar); cudaFree(K->d_abort);
+  for (int h = 0; h < 2; h++) {
+    cudaFree(K->p2p[h].d_wbase); cudaFree(K->p2p[h].d_rec);
+  }
   delete K;
 }
 
@@ -631,6 +794,11 @@ extern "C" int psp_prec_apply(psp_prec *K, const double *x, double *y) {
   PSP_TRY(prec_apply_dev(K, K->d_x, K->d_y, nullptr));
   PSP_CUDA(cudaEventRecord(c.ev1, c.stream));
   PSP_TRY(psp_vec_download(K->d_y, y, n, 1));
+  if (K->d_abort) {
+    int gave_up = 0;
+    PSP_CUDA(cudaMemcpy(&gave_up, K->d_abort, sizeof(int), cudaMemcpyDeviceToHost));
+    if (gave_up) { set_error("ssor: a sweep gave up waiting for a row it depends on (NaN payload clash in the input?)"); return PSP_ERR_CUDA; }
+  }
   float ms = 0.f;
   cudaEventElapsedTime(&ms, c.ev0, c.ev1);
   c.last_ms = ms;

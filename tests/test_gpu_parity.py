@@ -290,7 +290,7 @@ def test_ssor_sweep_engines_agree_bit_for_bit(gpu, native, checker, matrix):
     So = checker.sss(n, *mat["sss"])
     zo = np.zeros(n); checker.precon(checker.ssor(So, 1.3, 2), x, zo)
     ref = None
-    for engine in (0, 1, 2, 3):
+    for engine in (0, 1, 2, 3, 4):
         native.set_option("ssor_engine", engine)
         try:
             S = gpu.sss(n, *mat["sss"])
