@@ -7,18 +7,22 @@ b = 1, x0 = 0, tol = 1e-10.  One "step" = one complete solve.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--grid 256]
 
-* value   : PCG iterations per second, vectors and matrix resident in HBM
-            (psp_solve_dev), timed with CUDA events on the library stream;
-* e2e     : the same solve through the host-buffer API call (krylov.pcg /
-            psp_solve: b, x0 copied host->device from pinned memory, x copied
-            back) inside the timed region;
-* roofline: the fused SpMV+dot kernel (dominant kernel), sampled live with CUDA
-            event pairs inside the solver loop; algorithmic bytes
-            12 nnz + 4 (N+1) + 16 N per launch (SURVEY.md 8(d));
+* value   : PCG iterations per second with matrix and vectors resident in HBM (psp_solve_dev),
+            timed with CUDA events on the library stream;
+* e2e     : the same solve through the plug-in call a PySparse user makes,
+            krylov.pcg(A, b, x, tol, maxit, K) with ordinary pageable NumPy arrays: b, x0 copied
+            host->device and x copied back inside the timed region;
+* roofline: the persistent solver kernel (one cooperative launch per solve and GPU), algorithmic
+            bytes per iteration 12 nnz + 4 (N+1) + 104 N (SURVEY.md 8(d));
+* pcg_sss : the same solve on the sss_mat form; spmv: the SpMV half of the metric (BASELINE
+            config 2 and 5b: csr / csr transposed / sss on 128^3..384^3 and the power-law matrix,
+            device-resident and end to end through A.matvec(x, y));
 * cpu_baseline: the reference's own C kernels (oracle/_ref) on one host core,
             first CPU_ITERS iterations of the same solve.
 
-N > 1 (torchrun): the same system row-sharded over N GPUs (strong scaling).
+N > 1: ONE process drives N GPUs through the same plug-in call (option "gpus" / PSP_GPUS,
+psp_multi.cu): the system is cut into N row slabs (strong scaling).  Under torchrun rank 0 does
+that, the other ranks only take part in the barriers and the max-over-ranks reduction.
 """
 from __future__ import annotations
 
@@ -48,7 +52,9 @@ def parse():
     ap.add_argument("--tol", type=float, default=1e-10)
     ap.add_argument("--maxit", type=int, default=5000)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--sweep", action="store_true", help="also report the SpMV sweep (csr/sss, 128^3..)")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the SpMV half of the metric (config 2 / 5b)")
+    ap.add_argument("--sweep-sizes", default="128,256,384", help="3-D Poisson grids of the SpMV sweep (512 fits too: about 2 more minutes)")
+    ap.add_argument("--powerlaw-rows", type=int, default=1 << 21, help="rows of the power-law SpMV matrix (config 5b: 4194304); 0: skip")
     return ap.parse_args()
 
 
@@ -166,20 +172,25 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-# --------------------------------------------------------------------------- B200 arm, single GPU
-def run_single(args):
+# --------------------------------------------------------------------------- B200 arm
+def run_b200(args, world=1):
+    """One Python process drives `world` GPUs through the unchanged PySparse API (option "gpus",
+    psp_multi.cu).  Under torchrun only rank 0 gets here; the other ranks take part in the
+    barriers of main()."""
     from pysparse_b200 import _abi as P
-    if P.device_count() == 0:
-        raise SystemExit("bench.py: no CUDA device (pysparse_b200 has no CPU fallback)")
+    if P.device_count() < world:
+        raise SystemExit(f"bench.py: {world} CUDA device(s) needed, {P.device_count()} visible (pysparse_b200 has no CPU fallback)")
+    from pysparse_b200.itsolvers import krylov
+    from pysparse_b200.sparse import spmatrix
+    from pysparse_b200.precon import precon
     peak, peak_src = peaks()
+    P.set_option("gpus", world)
     N, val, col, ind, diag = build_problem(args.grid)
     nnz = int(len(val))
     A = P.Matrix.csr(N, N, val, col, ind)
     K = P.Precon.jacobi(A, diag)
     db = P.DeviceVector(N, np.ones(N))
     dx = P.DeviceVector(N)
-    hb = P.pinned_empty(N); hb[:] = 1.0
-    hx = P.pinned_empty(N)
 
     def dev_step():
         dx.fill(0.0)
@@ -189,36 +200,34 @@ def run_single(args):
         res = dev_step()
     P.synchronize()
 
-    clocks = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    clocks = ClockSampler(0)
     clocks.start()
-    P.spmv_timing(8)                     # sample every 8th SpMV launch from here on
     P.launch_count(reset=True)
     P.synchronize()
     P.event_record(0)
-    iters = 0
+    iters, dev_ms = 0, 0.0
     for _ in range(args.steps):
         res = dev_step()
         iters += res[1]
+        dev_ms += P.last_device_ms()
     P.event_record(1)
     P.synchronize()
     ms = P.event_elapsed_ms(0, 1)
     launches = P.launch_count()
-    n_spmv, spmv_ms = P.spmv_timing(0)
     clk = clocks.stop()
 
-    # end to end through the host-buffer call (pinned host arrays)
-    e2e_step_fn = lambda: (hx.__setitem__(slice(None), 0.0), P.solve("pcg", A, hb, hx, args.tol, args.maxit, K))[1]
-    api = "psp_solve (C-ABI, host buffers)"
-    try:
-        from pysparse_b200.itsolvers import krylov
-        from pysparse_b200.sparse import spmatrix
-        from pysparse_b200.precon import precon
-        Am = spmatrix.csr_from_arrays(N, N, ind, col, val)
-        Km = precon.jacobi(Am)
-        e2e_step_fn = lambda: (hx.__setitem__(slice(None), 0.0), krylov.pcg(Am, hb, hx, args.tol, args.maxit, Km))[1]
-        api = "pysparse_b200.itsolvers.krylov.pcg(A, b, x, tol, maxit, K) with NumPy arrays"
-    except (ImportError, AttributeError):
-        pass
+    # end to end: the plug-in call itself, with ordinary (pageable) NumPy arrays, as a PySparse
+    # user makes it -- b and x0 go host -> device(s), x comes back, all inside the timed region
+    Am = spmatrix.csr_from_arrays(N, N, ind, col, val)
+    Km = precon.jacobi(Am)
+    hb = np.ones(N)
+    hx = np.zeros(N)
+    api = "pysparse_b200.itsolvers.krylov.pcg(A, b, x, tol, maxit, K) with pageable NumPy arrays"
+
+    def e2e_step_fn():
+        hx[:] = 0.0
+        return krylov.pcg(Am, hb, hx, args.tol, args.maxit, Km)
+
     e2e_step_fn()
     P.synchronize()
     t0 = time.perf_counter()
@@ -228,101 +237,152 @@ def run_single(args):
         e2e_iters += r2[1]
     P.synchronize()
     e2e_s = time.perf_counter() - t0
+    del Am, Km
 
+    nl = N // world                                   # rows of one rank's slab
+    par = "1 GPU" if world == 1 else (f"{world} GPUs driven by one process: contiguous row slabs, boundary values pushed over "
+                                      f"NVLink peer memory inside the solver kernel, in-kernel all-reduce (no collective library)")
     line = {
-        "metric": "pcg_iters_per_s", "value": iters / (ms * 1e-3), "unit": "iter/s", "n_gpus": 1,
+        "metric": "pcg_iters_per_s", "value": iters / (ms * 1e-3), "unit": "iter/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"3-D 7-point Poisson {args.grid}^3, PCG + Jacobi, tol {args.tol:g}, b=1, x0=0",
-                   "rows": N, "nnz": nnz, "format": "csr", "parallelism": "1 GPU",
-                   "l2_policy": "inputs larger than L2 (matrix 1.47 GB + 6 vectors of 134 MB vs 126 MB L2)",
+                   "rows": N, "nnz": nnz, "format": "csr", "parallelism": par,
+                   "device_layout": "diagonal runs (values only; no column indices on the device)",
+                   "l2_policy": "inputs larger than L2 (matrix values 0.94 GB + 6 vectors of 134 MB vs 126 MB L2)" if N * 8 * 6 / world > 126e6
+                                else "per-GPU working set may fit in L2 at this N (strong scaling)",
                    "result": {"info": res[0], "iter": res[1], "relres": res[2]}},
         "e2e": {"value": e2e_iters / e2e_s, "unit": "iter/s", "h2d_bytes_per_step": 16 * N,
-                "d2h_bytes_per_step": 8 * N + 16, "api": api, "seconds_per_step": e2e_s / args.steps},
+                "d2h_bytes_per_step": 8 * N, "api": api, "host_memory": "pageable", "seconds_per_step": e2e_s / args.steps},
         "gpu_launches": launches,
         "clocks": clk,
         "iters_per_step": iters / args.steps,
-        "pcg_iter_algorithmic_GBps": alg_bytes_pcg_iter(N, nnz) * iters / (ms * 1e-3) / 1e9,
+        "solver_kernel_ms_per_step": dev_ms / args.steps,
     }
+
     def traffic_of(key):
         tp = os.path.join(ROOT, "profiles", "spmv_traffic.json")
-        if os.path.exists(tp) and args.grid == 256:
+        if os.path.exists(tp) and args.grid == 256 and world == 1:
             return json.load(open(tp)).get(key)
         return None
 
-    def spmv_roofline(n_spmv, spmv_ms):
-        per = spmv_ms / n_spmv * 1e-3
-        ach = alg_bytes_spmv(N, nnz) / per / 1e9
-        return {"bound": "hbm", "kernel": "k_spmv_tma<2,true> (CSR SpMV + fused p.q dot)",
-                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": traffic_of("dram_bytes_per_launch"), "peak_source": peak_src, "launches_sampled": n_spmv,
-                "avg_launch_us": per * 1e6, "algorithmic_bytes_per_launch": alg_bytes_spmv(N, nnz),
-                "gflops": 2 * nnz / per / 1e9}
-
-    if n_spmv:
-        line["roofline"] = spmv_roofline(n_spmv, spmv_ms)
-    else:
-        # The solve ran as ONE persistent cooperative kernel (k_pcg_persist): that launch is
-        # the dominant kernel.  Algorithmic bytes per launch = iterations x the per-iteration
-        # figure of DESIGN.md (matrix once + 13 vector streams); duration = the CUDA-event
-        # time of the timed region / launches (it contains nothing else but a memset).
-        per = ms * 1e-3 / args.steps
-        nb = alg_bytes_pcg_iter(N, nnz) * iters / args.steps
-        line["roofline"] = {"bound": "hbm", "kernel": "k_pcg_persist (whole PCG + Jacobi solve in one cooperative launch)",
-                            "achieved": nb / per / 1e9, "peak": peak, "unit": "GB/s", "frac": nb / per / 1e9 / peak,
-                            "traffic": traffic_of("pcg_persist_dram_bytes_per_launch"), "peak_source": peak_src,
-                            "launches_sampled": args.steps, "avg_launch_us": per * 1e6,
-                            "algorithmic_bytes_per_launch": nb,
-                            "algorithmic_bytes_per_iteration": alg_bytes_pcg_iter(N, nnz)}
-        # for continuity: the stand-alone SpMV + dot kernel, sampled in a short solve on the
-        # per-phase path (not part of the timed region)
-        P.set_option("pcg_persist", 0)
-        dx.fill(0.0)
-        P.solve("pcg", A, db, dx, args.tol, 32, K, dev=True)      # settle on the per-phase path first
-        P.spmv_timing(8)
-        dx.fill(0.0)
-        P.solve("pcg", A, db, dx, args.tol, 256, K, dev=True)
-        n2, ms2 = P.spmv_timing(0)
-        P.set_option("pcg_persist", -1)
-        if n2:
-            line["roofline_spmv"] = spmv_roofline(n2, ms2)
-    if args.sweep:
-        line["spmv_sweep"] = spmv_sweep(P)
-    if not args.no_cpu:
-        line["cpu_baseline"] = cpu_baseline(args, N, val, col, ind, diag)
-    print(json.dumps(line), flush=True)
+    # The solve is ONE persistent cooperative kernel per GPU (k_pcg_persist): that launch is the
+    # dominant kernel.  Algorithmic bytes per launch = iterations x the per-iteration figure of
+    # DESIGN.md / SURVEY 8(d) (CSR matrix once + 13 vector streams) for one rank's slab; duration =
+    # the CUDA-event time of that launch (psp_last_device_ms: max over the ranks), against ONE
+    # GPU's measured peak.  The kernel moves FEWER bytes than the algorithmic figure (no column
+    # indices: 8 instead of 12 bytes per entry), which is how frac can approach or pass 1.
+    per = dev_ms * 1e-3 / args.steps
+    nb = alg_bytes_pcg_iter(nl, nnz // world) * iters / args.steps
+    line["roofline"] = {"bound": "hbm", "kernel": "k_pcg_persist<1> (whole PCG + Jacobi solve in one cooperative launch per GPU, diagonal-run matrix format)",
+                        "achieved": nb / per / 1e9, "peak": peak, "unit": "GB/s", "frac": nb / per / 1e9 / peak,
+                        "traffic": traffic_of("pcg_persist_runs_dram_bytes_per_launch"), "peak_source": peak_src,
+                        "launches_sampled": args.steps, "avg_launch_us": per * 1e6,
+                        "algorithmic_bytes_per_launch": nb,
+                        "algorithmic_bytes_per_iteration": alg_bytes_pcg_iter(nl, nnz // world),
+                        "moved_bytes_per_iteration_by_design": 8 * (nnz // world) + 104 * nl}
+    if world == 1:
+        line["pcg_sss"] = pcg_sss(P, args, peak)
+        if not args.no_sweep:
+            line["spmv"] = spmv_sweep(P, args)
+        if not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline(args, N, val, col, ind, diag)
+    P.set_option("gpus", 1)
+    return line
 
 
-def spmv_sweep(P, sizes=(128, 192, 256)):
+def pcg_sss(P, args, peak):
+    """The same solve on the sss_mat form of the matrix (the reference's idiom for symmetric
+    systems: examples/poisson_test.py solves on L.to_sss())."""
     from pysparse_b200.tools import gallery as g
+    mat = g.poisson3d(args.grid, want_csr=False, want_sss=True)
+    N = mat["n"]
+    val, diag, col, ind = mat["sss"]
+    S = P.Matrix.sss(N, val, diag, col, ind)
+    K = P.Precon.jacobi(None, diag)
+    db = P.DeviceVector(N, np.ones(N)); dx = P.DeviceVector(N)
+    ms, iters = 0.0, 0
+    for rep in range(1 + args.steps):
+        dx.fill(0.0)
+        r = P.solve("pcg", S, db, dx, args.tol, args.maxit, K, dev=True)
+        if rep:
+            ms += P.last_device_ms(); iters += r[1]
+    nb = 12 * len(val) + 4 * (N + 1) + 8 * N + 104 * N          # SURVEY 8(d): SSS matrix once + 13 vector streams
+    return {"value": iters / (ms * 1e-3), "unit": "iter/s", "result": {"info": r[0], "iter": r[1], "relres": r[2]},
+            "algorithmic_bytes_per_iteration": nb, "achieved_GBps": nb * iters / (ms * 1e-3) / 1e9,
+            "frac": nb * iters / (ms * 1e-3) / 1e9 / peak}
+
+
+def spmv_sweep(P, args):
+    """BASELINE config 2 (+ 5b): device-resident csr_mat / sss_mat matvec and csr matvec_transp on
+    3-D Poisson grids, the power-law matrix, and the same product end to end through
+    A.matvec(x, y) with pageable NumPy arrays."""
+    from pysparse_b200.tools import gallery as g
+    from pysparse_b200.sparse import spmatrix
     out = []
     rng = np.random.default_rng(0)
     peak, _ = peaks()
+
+    def timed(A, dx, dy, transp=False, reps=30):
+        for _ in range(4):
+            A.matvec_dev(dx, dy, transp)
+        P.event_record(2)
+        for _ in range(reps):
+            A.matvec_dev(dx, dy, transp)
+        P.event_record(3)
+        return P.event_elapsed_ms(2, 3) * 1e-3 / reps
+
+    def e2e(Am, m, n, transp=False, reps=3):
+        x = rng.standard_normal(m if transp else n); y = np.empty(n if transp else m)
+        f = Am.matvec_transp if transp else Am.matvec
+        f(x, y)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            f(x, y)
+        return (time.perf_counter() - t0) / reps
+
+    sizes = [int(v) for v in args.sweep_sizes.split(",") if v]
     for n in sizes:
         mat = g.poisson3d(n)
         N = mat["n"]
-        for fmt in ("csr", "sss"):
-            if fmt == "csr":
-                val, col, ind = mat["csr"]
-                A = P.Matrix.csr(N, N, val, col, ind)
-                nb = alg_bytes_spmv(N, len(val)); flops = 2 * len(val)
-            else:
-                val, diag, col, ind = mat["sss"]
-                A = P.Matrix.sss(N, val, diag, col, ind)
-                nb = 12 * len(val) + 4 * (N + 1) + 24 * N; flops = 4 * len(val) + 2 * N
-            dx = P.DeviceVector(N, rng.standard_normal(N)); dy = P.DeviceVector(N)
-            for _ in range(5):
-                A.matvec_dev(dx, dy)
-            P.synchronize()
-            P.event_record(2)
-            reps = 50
-            for _ in range(reps):
-                A.matvec_dev(dx, dy)
-            P.event_record(3)
-            dt = P.event_elapsed_ms(2, 3) * 1e-3 / reps
-            out.append({"n": n, "format": fmt, "us": dt * 1e6, "GBps_algorithmic": nb / dt / 1e9,
-                        "frac_of_peak": nb / dt / 1e9 / peak, "GFLOPs": flops / dt / 1e9})
-            del A, dx, dy
+        dx = P.DeviceVector(N, rng.standard_normal(N)); dy = P.DeviceVector(N)
+        val, col, ind = mat["csr"]
+        A = P.Matrix.csr(N, N, val, col, ind)
+        nb = alg_bytes_spmv(N, len(val)); flops = 2 * len(val)
+        for what, tr in (("csr", False), ("csr_transp", True)):
+            dt = timed(A, dx, dy, tr)
+            rec = {"matrix": f"poisson3d {n}^3", "op": what, "us": dt * 1e6, "GBps_algorithmic": nb / dt / 1e9,
+                   "frac": nb / dt / 1e9 / peak, "GFLOPs": flops / dt / 1e9}
+            if n <= 256:
+                Am = spmatrix.csr_from_arrays(N, N, ind, col, val)
+                rec["e2e_ms_pageable_numpy"] = e2e(Am, N, N, tr) * 1e3
+                del Am
+            out.append(rec)
+        del A
+        val, diag, col, ind = mat["sss"]
+        S = P.Matrix.sss(N, val, diag, col, ind)
+        nb = 12 * len(val) + 4 * (N + 1) + 24 * N; flops = 4 * len(val) + 2 * N
+        dt = timed(S, dx, dy)
+        rec = {"matrix": f"poisson3d {n}^3", "op": "sss", "us": dt * 1e6, "GBps_algorithmic": nb / dt / 1e9,
+               "frac": nb / dt / 1e9 / peak, "GFLOPs": flops / dt / 1e9}
+        if n <= 256:
+            Sm = spmatrix.sss_from_arrays(N, ind, col, val, diag)
+            rec["e2e_ms_pageable_numpy"] = e2e(Sm, N, N) * 1e3
+            del Sm
+        out.append(rec)
+        del S, dx, dy, mat
+    if args.powerlaw_rows:
+        mat = g.powerlaw(args.powerlaw_rows)
+        m, n = mat["shape"] if "shape" in mat else (mat["n"], mat["n"])
+        val, col, ind = mat["csr"]
+        A = P.Matrix.csr(m, n, val, col, ind)
+        dx = P.DeviceVector(n, rng.standard_normal(n)); dy = P.DeviceVector(m)
+        nb = 12 * len(val) + 4 * (m + 1) + 8 * n + 8 * m
+        for what, tr in (("csr", False), ("csr_transp", True)):
+            dt = timed(A, dx, dy, tr, reps=10)
+            out.append({"matrix": f"power-law rows {m} (mean {len(val) / m:.1f}, max {int(np.diff(ind).max())} entries per row)",
+                        "op": what, "us": dt * 1e6, "GBps_algorithmic": nb / dt / 1e9, "frac": nb / dt / 1e9 / peak,
+                        "GFLOPs": 2 * len(val) / dt / 1e9})
     return out
 
 
@@ -346,10 +406,36 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.gpus > 1 or world > 1:
-        from pysparse_b200 import dist_bench
-        return dist_bench.run(args, sys.modules[__name__])
-    return run_single(args)
+    rank = int(os.environ.get("RANK", "0"))
+    n_gpus = max(args.gpus, world)
+    dist = ctl = None
+    if world > 1:
+        # torchrun launches one process per GPU; ONE process (rank 0) drives all the GPUs through
+        # the plug-in API, the others hold their place in the launch protocol: barrier before
+        # and after, and the max-over-ranks reduction of the timed region.  They wait on a CPU
+        # (gloo) barrier: an NCCL barrier would park a spinning kernel on every GPU, and the
+        # persistent solver kernels are cooperative launches that need all SMs of their GPU.
+        import torch
+        import torch.distributed as dist
+        local = int(os.environ.get("LOCAL_RANK", str(rank)))
+        torch.cuda.set_device(local)
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+        ctl = dist.new_group(backend="gloo")
+        dist.barrier()
+        torch.cuda.synchronize()
+        dist.barrier(group=ctl)
+    line = run_b200(args, n_gpus) if rank == 0 else None
+    if world > 1:
+        import torch
+        dist.barrier(group=ctl)
+        torch.cuda.synchronize()
+        t = torch.tensor([line["ms_per_step"] if line else 0.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if line:
+            line["ms_per_step"] = float(t.item())
+        dist.destroy_process_group()
+    if line:
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

@@ -84,6 +84,17 @@ int psp_mat_info(const psp_mat *a, int *m, int *n, long long *nnz, int *kind);
  * (sss_mat.c:40-76) behind CSRMat_matvec / SSSMat_matvec. */
 int psp_matvec(psp_mat *a, int transp, const double *x, long incx, double *y, long incy);
 
+/* Host-only analysis behind the "diagonal run" device layout of a matrix (csrc/psp_runs.cuh): the
+ * rows of csr_matvec_kernel / sss_matvec re-expressed as runs of consecutive rows on one diagonal.
+ * sss = 0: CSR arrays (diag ignored); sss = 1: strict lower triangle + diagonal, every stored
+ * value kept once and referenced by two run descriptors.  Outputs (malloc'ed, release with
+ * psp_runs_free): blk[4 nblk] = (first row, rows, first run, end run), seg[4 nseg] = (position of
+ * the first value, first column, first local row, length), rval[nval].  Bit-exact structure
+ * work; needs no GPU (the CPU tests rebuild the matrix from it). */
+int psp_runs_analyze(int sss, int m, const int *ind, const int *col, const double *val, const double *diag,
+                     int *nblk, int *nseg, long long *nval, int **blk, int **seg, double **rval);
+void psp_runs_free(void *p);
+
 /* same with DEVICE vectors (contiguous); asynchronous on the library stream */
 int psp_matvec_dev(psp_mat *a, int transp, const double *dx, double *dy);
 

@@ -24,7 +24,7 @@ SYMBOLS = [
     "psp_init", "psp_device_count", "psp_current_device", "psp_last_error", "psp_version",
     "psp_launch_count", "psp_synchronize", "psp_host_alloc", "psp_host_free",
     "psp_csr_create", "psp_sss_create", "psp_mat_destroy", "psp_mat_info",
-    "psp_matvec", "psp_matvec_dev",
+    "psp_matvec", "psp_matvec_dev", "psp_runs_analyze", "psp_runs_free",
     "psp_vec_alloc", "psp_vec_free", "psp_vec_upload", "psp_vec_download", "psp_vec_fill",
     "psp_jacobi_create", "psp_ssor_create", "psp_prec_destroy", "psp_prec_apply",
     "psp_prec_apply_dev", "psp_ssor_levels", "psp_prec_set_matrix",

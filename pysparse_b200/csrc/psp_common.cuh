@@ -126,7 +126,17 @@ struct Ctx {
   size_t pool_cap[3] = {0, 0, 0};
   // options
   long long spmv_variant = 0;
+  long long gpus = 1;         // > 1: matrices are also cut into row slabs over that many GPUs and pcg / bicgstab / gmres run sharded (PSP_GPUS)
   long long spmv_format = -1; // device layout chosen at matrix creation: -1 automatic, 0 CSR row blocks, 1 diagonal runs
+  // per-device launch caches (occupancy, "attribute already set"): a context is one device, and
+  // cudaFuncSetAttribute is per device -- nothing of this kind may live in a function-static
+  int occ_tma[2][2] = {{0, 0}, {0, 0}}, occ_tma_cap[2][2] = {{-1, -1}, {-1, -1}};   // k_spmv_tma<STAGES-2, DOTS>
+  int occ_stream[2][2] = {{0, 0}, {0, 0}};                                          // k_spmv_stream<VEC, DOTS>
+  int occ_sweep_grid[2] = {0, 0};
+  size_t sweep_cta_smem[2] = {0, 0};
+  bool sweep_cluster_ready[2] = {false, false};
+  double *persist_partials = nullptr;           // scratch of the persistent kernels' all-reduce
+  void *persist_sync = nullptr;
   int occ_runs[2] = {0, 0};   // resident CTAs of k_spmv_runs<false/true> on this device
   int occ_pcg[2] = {0, 0};    // resident CTAs of k_pcg_persist<format> on this device
   int occ_bicg[2] = {0, 0}, occ_gmres[2] = {0, 0};
@@ -149,7 +159,9 @@ struct Ctx {
   cudaEvent_t user_ev[8] = {};
 };
 
-Ctx &ctx();
+Ctx &ctx();                          // the calling thread's context (a rank of the in-process multi-GPU layer has its own)
+void bind_thread(Ctx *c, struct DistHost *d);   // psp_multi.cu: make a worker thread act as one rank
+int init_ctx(Ctx &c, int device);    // create streams / scratch of a context on `device`
 int ensure_init();                   // PSP_OK or error; lazily initialises device 0
 int ensure_stage(size_t elems);      // pinned staging buffer of at least `elems` doubles
 int pool_get(int slot, size_t elems, double **out);   // context-owned device scratch (grows, never shrinks below use)

@@ -21,7 +21,10 @@
 namespace psp {
 
 static DistHost g_dist;
-DistHost &dist() { return g_dist; }
+static thread_local DistHost *t_dist = nullptr;    // set in the rank threads of the in-process multi-GPU layer
+DistHost &dist() { return t_dist ? *t_dist : g_dist; }
+void set_thread_ctx(Ctx *c);
+void bind_thread(Ctx *c, DistHost *d) { set_thread_ctx(c); t_dist = d; }
 
 __global__ void __launch_bounds__(kThreads) k_halo_pull(State *S, size_t slot_off, const int *owner,
                                                         const int *ridx, int nhalo, int nl, double *xloc,
@@ -50,7 +53,7 @@ __global__ void __launch_bounds__(kThreads) k_halo_pull(State *S, size_t slot_of
 
 int dist_pull(DistMat *dm, double *xloc, int gate) {
   Ctx &c = ctx();
-  DistHost &d = g_dist;
+  DistHost &d = dist();
   int grid = (dm->nhalo + kThreads - 1) / kThreads;
   if (grid < 1) grid = 1;
   if (grid > 2 * c.sms) grid = 2 * c.sms;
@@ -118,7 +121,7 @@ extern "C" int psp_dist_init(int rank, int world, size_t slot_elems, int nslots,
     return PSP_ERR_ARG;
   }
   PSP_TRY(ensure_init());
-  DistHost &d = g_dist;
+  DistHost &d = dist();
   if (d.ready) { set_error("psp_dist_init: already initialised"); return PSP_ERR_DIST; }
   d.rank = rank; d.world = world; d.slot_elems = slot_elems; d.nslots = nslots;
   // nslots work vectors, then the flag-in-data halo landing zone of the persistent kernels:
@@ -136,7 +139,7 @@ extern "C" int psp_dist_init(int rank, int world, size_t slot_elems, int nslots,
 }
 
 extern "C" int psp_dist_connect(const void *all_handles) {
-  DistHost &d = g_dist;
+  DistHost &d = dist();
   if (!d.heap || !all_handles) { set_error("psp_dist_connect: call psp_dist_init first"); return PSP_ERR_DIST; }
   const cudaIpcMemHandle_t *h = (const cudaIpcMemHandle_t *)all_handles;
   DistDev dd;
@@ -164,10 +167,10 @@ extern "C" int psp_dist_connect(const void *all_handles) {
 }
 
 extern "C" int psp_dist_shutdown(void) {
-  DistHost &d = g_dist;
+  DistHost &d = dist();
   if (!d.heap) return PSP_OK;
   cudaDeviceSynchronize();
-  for (int w = 0; w < d.world; w++)
+  for (int w = 0; w < d.world && !d.in_process; w++)
     if (w != d.rank) {
       if (d.peer_heap[w]) cudaIpcCloseMemHandle(d.peer_heap[w]);
       if (d.peer_ctl[w]) cudaIpcCloseMemHandle(d.peer_ctl[w]);
@@ -177,8 +180,56 @@ extern "C" int psp_dist_shutdown(void) {
   return PSP_OK;
 }
 
+// ---- in-process variants (psp_multi.cu: one thread per GPU in ONE process; peer access instead
+// of CUDA IPC -- with unified addressing the peers' allocations are directly addressable)
+namespace psp {
+
+int dist_local_alloc(int rank, int world, size_t slot_elems, int nslots) {
+  DistHost &d = dist();
+  if (d.heap) { set_error("dist_local_alloc: heap already exists"); return PSP_ERR_DIST; }
+  d.rank = rank; d.world = world; d.slot_elems = slot_elems; d.nslots = nslots; d.in_process = true;
+  const size_t heap_bytes = sizeof(double) * (ll_offset(slot_elems, nslots) + 2 * slot_elems);
+  if (cudaMalloc((void **)&d.heap, heap_bytes ? heap_bytes : 8) != cudaSuccess) {
+    cudaGetLastError();
+    set_error("multi-GPU: cannot allocate the %zu-byte symmetric heap on device %d", heap_bytes, ctx().device);
+    return PSP_ERR_NOMEM;
+  }
+  PSP_CUDA(cudaMemset(d.heap, 0, heap_bytes ? heap_bytes : 8));
+  PSP_CUDA(cudaMalloc((void **)&d.ctl, sizeof(DistCtl)));
+  PSP_CUDA(cudaMemset(d.ctl, 0, sizeof(DistCtl)));
+  return PSP_OK;
+}
+
+// all[w]: the DistHost of rank w (its heap / ctl pointers are valid on every device)
+int dist_local_connect(DistHost *const *all) {
+  DistHost &d = dist();
+  DistDev dd;
+  memset(&dd, 0, sizeof dd);
+  dd.rank = d.rank; dd.world = d.world;
+  dd.ll_off = ll_offset(d.slot_elems, d.nslots);
+  for (int w = 0; w < d.world; w++) {
+    d.peer_heap[w] = all[w]->heap; d.peer_ctl[w] = all[w]->ctl;
+    dd.heap[w] = d.peer_heap[w]; dd.ctl[w] = d.peer_ctl[w];
+  }
+  PSP_CUDA(cudaMalloc((void **)&d.dev, sizeof(DistDev)));
+  PSP_CUDA(cudaMemcpy(d.dev, &dd, sizeof dd, cudaMemcpyHostToDevice));
+  d.ready = true;
+  return PSP_OK;
+}
+
+int dist_local_free() {
+  DistHost &d = dist();
+  if (!d.heap) return PSP_OK;
+  cudaDeviceSynchronize();
+  cudaFree(d.heap); cudaFree(d.ctl); cudaFree(d.dev);
+  d = DistHost();
+  return PSP_OK;
+}
+
+}  // namespace psp
+
 extern "C" int psp_dist_info(int *rank, int *world, size_t *slot_elems, int *nslots) {
-  DistHost &d = g_dist;
+  DistHost &d = dist();
   if (rank) *rank = d.rank;
   if (world) *world = d.world;
   if (slot_elems) *slot_elems = d.slot_elems;
@@ -191,25 +242,50 @@ namespace psp {
 int csr_create(int, int, long long, const int *, const int *, const double *, psp_mat **, bool, int, const int *, int);
 }
 
-extern "C" int psp_dist_csr_create(const int *rowptr, int nnz, const int *ind, const int *col_global,
-                                   const double *val, psp_dmat **out) {
-  DistHost &d = g_dist;
-  if (!d.ready) { set_error("psp_dist_csr_create: distributed layer not initialised"); return PSP_ERR_DIST; }
-  if (!rowptr || !ind || !out) { set_error("psp_dist_csr_create: NULL argument"); return PSP_ERR_ARG; }
-  const int nl = rowptr[d.rank + 1] - rowptr[d.rank];
+namespace psp {
+int dist_csr_finish(DistMat *dm, const std::vector<int> &owner, const std::vector<int> &ridx, int nhalo);
+// Slab of rank `rank`: local column numbering, device upload, halo tables.  Independent of the
+// symmetric heap (the caller checks that nl + nhalo fits a slot).  owner_out / ridx_out: the
+// halo lists (host copies) for building the send maps.
+int dist_csr_build(int world, int rank, const int *rowptr, int nnz, const int *ind, const int *col_global,
+                   const double *val, DistMat **out, std::vector<int> *owner_out, std::vector<int> *ridx_out) {
+  const int nl = rowptr[rank + 1] - rowptr[rank];
   if (ind[nl] != nnz) { set_error("psp_dist_csr_create: ind[nl] != nnz"); return PSP_ERR_ARG; }
   std::vector<int> col_local((size_t)(nnz > 0 ? nnz : 1)), owner((size_t)(nnz > 0 ? nnz : 1)), ridx((size_t)(nnz > 0 ? nnz : 1));
   int nhalo = 0;
-  PSP_TRY(psp_dist_plan(d.world, d.rank, rowptr, nl, ind, col_global, col_local.data(), nullptr, owner.data(),
+  PSP_TRY(psp_dist_plan(world, rank, rowptr, nl, ind, col_global, col_local.data(), nullptr, owner.data(),
                         ridx.data(), &nhalo));
-  if ((size_t)nl + (size_t)nhalo > d.slot_elems) {
-    set_error("psp_dist_csr_create: local rows + halo (%d + %d) exceed the heap slot size %zu", nl, nhalo, d.slot_elems);
+  DistMat *dm = new DistMat();
+  dm->nl = nl; dm->nhalo = nhalo; dm->nglobal = rowptr[world];
+  int st = csr_create(nl, nl + nhalo, nnz, ind, col_local.data(), val, &dm->local, false, nl, col_global, rowptr[rank]);
+  if (st != PSP_OK) { delete dm; return st; }
+  st = dist_csr_finish(dm, owner, ridx, nhalo);
+  if (st != PSP_OK) return st;
+  if (owner_out) owner_out->assign(owner.begin(), owner.begin() + nhalo);
+  if (ridx_out) ridx_out->assign(ridx.begin(), ridx.begin() + nhalo);
+  *out = dm;
+  return PSP_OK;
+}
+}  // namespace psp
+
+extern "C" int psp_dist_csr_create(const int *rowptr, int nnz, const int *ind, const int *col_global,
+                                   const double *val, psp_dmat **out) {
+  DistHost &d = dist();
+  if (!d.ready) { set_error("psp_dist_csr_create: distributed layer not initialised"); return PSP_ERR_DIST; }
+  if (!rowptr || !ind || !out) { set_error("psp_dist_csr_create: NULL argument"); return PSP_ERR_ARG; }
+  DistMat *dm = nullptr;
+  PSP_TRY(dist_csr_build(d.world, d.rank, rowptr, nnz, ind, col_global, val, &dm, nullptr, nullptr));
+  if ((size_t)dm->nl + (size_t)dm->nhalo > d.slot_elems) {
+    set_error("psp_dist_csr_create: local rows + halo (%d + %d) exceed the heap slot size %zu", dm->nl, dm->nhalo, d.slot_elems);
+    psp_dist_mat_destroy((psp_dmat *)dm);
     return PSP_ERR_ARG;
   }
-  DistMat *dm = new DistMat();
-  dm->nl = nl; dm->nhalo = nhalo; dm->nglobal = rowptr[d.world];
-  int st = csr_create(nl, nl + nhalo, nnz, ind, col_local.data(), val, &dm->local, false, nl, col_global, rowptr[d.rank]);
-  if (st != PSP_OK) { delete dm; return st; }
+  *out = (psp_dmat *)dm;
+  return PSP_OK;
+}
+
+namespace psp {
+int dist_csr_finish(DistMat *dm, const std::vector<int> &owner, const std::vector<int> &ridx, int nhalo) {
   dm->nbmask = 0;
   for (int h = 0; h < nhalo; h++) dm->nbmask |= 1u << owner[h];
   const size_t hb = sizeof(int) * (size_t)(nhalo > 0 ? nhalo : 1);
@@ -223,9 +299,9 @@ extern "C" int psp_dist_csr_create(const int *rowptr, int nnz, const int *ind, c
     PSP_CUDA(cudaMemcpy(dm->d_owner, owner.data(), sizeof(int) * (size_t)nhalo, cudaMemcpyHostToDevice));
     PSP_CUDA(cudaMemcpy(dm->d_ridx, ridx.data(), sizeof(int) * (size_t)nhalo, cudaMemcpyHostToDevice));
   }
-  *out = (psp_dmat *)dm;
   return PSP_OK;
 }
+}  // namespace psp
 
 // Send map for the push model: entry s says "local row rows[s] is halo column number
 // off[s] - nl(dst) of rank dst_rank[s]", i.e. it has to be stored at element off[s] of the
@@ -234,7 +310,7 @@ extern "C" int psp_dist_csr_create(const int *rowptr, int nnz, const int *ind, c
 extern "C" int psp_dist_set_sendmap(psp_dmat *m, int nsend, const int *rows, const int *dst_rank,
                                     const int *dst_off) {
   DistMat *dm = (DistMat *)m;
-  DistHost &d = g_dist;
+  DistHost &d = dist();
   if (!dm || nsend < 0 || (nsend > 0 && (!rows || !dst_rank || !dst_off))) {
     set_error("psp_dist_set_sendmap: bad arguments");
     return PSP_ERR_ARG;

@@ -14,6 +14,7 @@ struct DistHost {
   double *peer_heap[kMaxRanks] = {};
   DistCtl *peer_ctl[kMaxRanks] = {};
   DistDev *dev = nullptr;                 // device copy of the descriptor
+  bool in_process = false;                // peers are threads of this process (peer access, no IPC mappings)
 };
 
 struct DistMat {
@@ -30,5 +31,12 @@ struct DistMat {
 
 DistHost &dist();
 int dist_pull(DistMat *dm, double *xloc, int gate = 0);
+int dist_local_alloc(int rank, int world, size_t slot_elems, int nslots);
+int dist_local_connect(DistHost *const *all);
+int dist_local_free();
+int dist_csr_build(int world, int rank, const int *rowptr, int nnz, const int *ind, const int *col_global,
+                   const double *val, DistMat **out, std::vector<int> *owner_out, std::vector<int> *ridx_out);
+int dist_solve_dev(int solver, DistMat *dm, psp_prec *K, const double *db, double *dx, double tol,
+                   int maxit, int gmres_dim, int *info, int *iter, double *relres);
 
 }  // namespace psp

@@ -1,6 +1,7 @@
 // psp_mat.cuh -- device-resident matrix / preconditioner objects.
 #pragma once
 #include "psp_common.cuh"
+#include "psp_multi.cuh"
 
 struct psp_mat {
   int kind = 0;             // 1 CSR, 2 SSS
@@ -37,6 +38,8 @@ struct psp_mat {
   // scratch vectors for the host-buffer entry points
   double *d_x = nullptr, *d_y = nullptr;
   size_t x_cap = 0, y_cap = 0;
+  // gpus > 1: the same matrix cut into row slabs, one per GPU (psp_multi.cu)
+  psp::MultiMat *multi = nullptr;
 };
 
 struct psp_prec {
@@ -46,6 +49,9 @@ struct psp_prec {
   int steps = 1;
   psp_mat *mat = nullptr;   // borrowed
   double *d_dinv = nullptr; // Jacobi
+  std::vector<double> h_dinv;               // host copy (the multi-GPU path uploads one slice per device)
+  std::vector<psp_prec *> multi_prec;       // per-rank slices, built on first use
+  std::vector<int> multi_rowptr;            // the row partition they were built for
   double *d_t1 = nullptr, *d_t2 = nullptr;
   // SSOR: level schedules
   int nlev_f = 0, nlev_b = 0;
@@ -89,9 +95,9 @@ struct SpmvDots {
 
 int spmv_launch(const psp_mat *a, const double *dx, double *dy, const SpmvDots &dots);
 int runs_launch(const psp_mat *a, const double *dx, double *dy, const SpmvDots &dots);   // psp_runs.cu
-// blocks per chunk of the run pass: as many as keep every resident CTA supplied with >= 2 chunks
+// blocks per chunk of the run pass (a chunk is the unit of work a CTA takes)
 inline int run_chunk(int nb, int resident_ctas) {
-  int c = resident_ctas > 0 ? nb / (2 * resident_ctas) : 1;
+  int c = resident_ctas > 0 ? nb / (8 * resident_ctas) : 1;       // >= 8 rounds: the last one costs little
   return c < 1 ? 1 : (c > 8 ? 8 : c);
 }
 // analysis + upload of the run format; *accepted = false leaves A untouched (psp_runs.cu).

@@ -245,14 +245,12 @@ __global__ void __launch_bounds__(kThreads, persist_ctas(FMT)) k_pcg_persist(Pcg
   }
 }
 
-static double *g_partials2 = nullptr;
-static PersistSync *g_sync = nullptr;
 
 int persist_prepare(PersistArgs &a, const psp_mat *M, int n, DistMat *dm) {
   Ctx &c = ctx();
-  if (!g_partials2) PSP_CUDA(cudaMalloc((void **)&g_partials2, sizeof(double) * 2 * (kRedSlots + 1) * kMaxGrid));
-  if (!g_sync) PSP_CUDA(cudaMalloc((void **)&g_sync, sizeof(PersistSync)));
-  PSP_CUDA(cudaMemsetAsync(g_sync, 0, sizeof(PersistSync), c.stream));
+  if (!c.persist_partials) PSP_CUDA(cudaMalloc((void **)&c.persist_partials, sizeof(double) * 2 * (kRedSlots + 1) * kMaxGrid));
+  if (!c.persist_sync) PSP_CUDA(cudaMalloc(&c.persist_sync, sizeof(PersistSync)));
+  PSP_CUDA(cudaMemsetAsync(c.persist_sync, 0, sizeof(PersistSync), c.stream));
   a.A.ind = M->d_ind; a.A.col = M->d_col; a.A.val = M->d_val; a.A.nb = M->nb;
   a.A.blk = reinterpret_cast<const int4 *>(M->d_blk);
   a.A.nint = M->nint;
@@ -261,7 +259,7 @@ int persist_prepare(PersistArgs &a, const psp_mat *M, int n, DistMat *dm) {
   a.R.blk = reinterpret_cast<const int4 *>(M->d_rblk); a.R.nb = M->nb; a.R.nint = M->nint;
   a.R.blk_halo = reinterpret_cast<const int2 *>(M->d_blk_halo);
   a.n = n;
-  a.S = c.state; a.partials = g_partials2; a.sync = g_sync; a.dd = dm ? dist().dev : nullptr;
+  a.S = c.state; a.partials = c.persist_partials; a.sync = static_cast<PersistSync *>(c.persist_sync); a.dd = dm ? dist().dev : nullptr;
   a.l2_stream = l2_stream_for(n); a.dist_debug = (int)c.dist_debug;
   a.halo_owner = dm ? dm->d_owner : nullptr; a.halo_ridx = dm ? dm->d_ridx : nullptr;
   a.nhalo = dm ? dm->nhalo : 0; a.nbmask = dm ? dm->nbmask : 0u;

@@ -347,8 +347,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) k_sweep_cta(SweepArgs a, const
 }
 
 static int grid_engine_blocks(const void *kernel) {
-  static int cached[2] = {0, 0};
-  int *slot = (kernel == (const void *)k_sweep_grid<false>) ? &cached[0] : &cached[1];
+  int *slot = (kernel == (const void *)k_sweep_grid<false>) ? &ctx().occ_sweep_grid[0] : &ctx().occ_sweep_grid[1];
   if (*slot == 0) {
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0) != cudaSuccess || per_sm < 1)
@@ -528,7 +527,7 @@ int prec_apply_dev(psp_prec *K, const double *dx, double *dy, State *gateS) {
   if (use_cta) {
     const void *kern = relax ? (const void *)k_sweep_cta<true> : (const void *)k_sweep_cta<false>;
     const size_t smem = sizeof(double) * 2 * (size_t)(maxw > 0 ? maxw : 1);
-    static size_t prepared_smem[2] = {0, 0};
+    size_t *prepared_smem = c.sweep_cta_smem;
     if (prepared_smem[relax ? 1 : 0] < smem) {
       PSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       prepared_smem[relax ? 1 : 0] = smem;
@@ -543,7 +542,7 @@ int prec_apply_dev(psp_prec *K, const double *dx, double *dy, State *gateS) {
   if (use_cluster) {
     const void *kern = relax ? (const void *)k_sweep_cluster<true> : (const void *)k_sweep_cluster<false>;
     int csize = (int)c.ssor_cluster;
-    static bool prepared[2] = {false, false};
+    bool *prepared = c.sweep_cluster_ready;
     if (!prepared[relax ? 1 : 0]) {
       PSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSweepSmem));
       PSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -739,9 +738,25 @@ extern "C" int psp_jacobi_create(psp_mat *A, int n, const double *diag, double o
     set_error("psp_jacobi_create: upload failed");
     return PSP_ERR_CUDA;
   }
+  if (multi_gpus() > 1) K->h_dinv.assign(dinv.begin(), dinv.begin() + n);
   *out = K;
   return PSP_OK;
 }
+
+namespace psp {
+// single-step Jacobi from a ready dinv slice (one rank of the multi-GPU path)
+int jacobi_from_dinv(int n, const double *dinv, psp_prec **out) {
+  psp_prec *K = new psp_prec();
+  K->kind = 1; K->n = n; K->omega = 1.0; K->steps = 1;
+  const size_t bytes = sizeof(double) * (size_t)(n > 0 ? n : 1);
+  if (cudaMalloc((void **)&K->d_dinv, bytes) != cudaSuccess) { cudaGetLastError(); delete K; set_error("jacobi: out of device memory"); return PSP_ERR_NOMEM; }
+  if (n > 0 && cudaMemcpy(K->d_dinv, dinv, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaGetLastError(); cudaFree(K->d_dinv); delete K; set_error("jacobi: upload failed"); return PSP_ERR_CUDA;
+  }
+  *out = K;
+  return PSP_OK;
+}
+}  // namespace psp
 
 extern "C" int psp_ssor_create(psp_mat *sss, double omega, int steps, psp_prec **out) {
   if (!out) { set_error("psp_ssor_create: NULL out"); return PSP_ERR_ARG; }
@@ -759,6 +774,7 @@ extern "C" int psp_prec_set_matrix(psp_prec *K, psp_mat *A) {
 
 extern "C" void psp_prec_destroy(psp_prec *K) {
   if (!K) return;
+  multi_prec_release(K);
   cudaFree(K->d_dinv); cudaFree(K->d_t1); cudaFree(K->d_t2);
   cudaFree(K->d_rows_f); cudaFree(K->d_lptr_f); cudaFree(K->d_rows_b); cudaFree(K->d_lptr_b);
   cudaFree(K->d_find); cudaFree(K->d_fcol); cudaFree(K->d_fval);

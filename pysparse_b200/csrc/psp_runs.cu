@@ -224,16 +224,19 @@ bool by_key_then_row(const Seg &a, const Seg &b) { return a.key != b.key ? a.key
 
 }  // namespace
 
-int runs_try_csr(psp_mat *A, const int *ind, const int *col, const double *val, const int *gcol, int grow0,
-                 int own_cols, bool *accepted) {
-  *accepted = false;
-  Ctx &c = ctx();
-  const int m = A->m;
+// Automatic choice: the run kernels win once the matrix stream is far beyond what L2 and the
+// latency of one pass can hide (measured on 3-D Poisson, PCG us/iteration, runs vs row blocks:
+// 192^3 255 vs 238, 256^3 493 vs 545; SpMV 256^3 228 vs 288 us) -- below ~1 GB of CSR stream
+// the TMA-fed row blocks stay the default.  `bytes`: 12 bytes per entry of the (expanded) matrix.
+static bool runs_pay_off(long long bytes) { return bytes >= (1LL << 30); }
+
+// host-only analysis of a CSR structure; `force`: build whatever the run lengths are
+static bool build_csr_runs(int m, const int *ind, const int *col, const double *val, const int *gcol, int grow0,
+                           bool force, RunBuild &rb) {
   const long long nnz = ind[m];
-  if (c.spmv_format == 0 || m == 0 || nnz == 0) return PSP_OK;
-  if (c.spmv_format < 0 && !sample_accepts(m, ind, col, gcol, grow0)) return PSP_OK;
+  if (m == 0 || nnz == 0) return false;
+  if (!force && !sample_accepts(m, ind, col, gcol, grow0)) return false;
   const int nb = (m + kThreads - 1) / kThreads;
-  RunBuild rb;
   rb.blk.resize(4 * (size_t)nb);
   rb.val.resize((size_t)nnz);
   std::vector<Seg> segs;
@@ -261,24 +264,32 @@ int runs_try_csr(psp_mat *A, const int *ind, const int *col, const double *val, 
         rb.val[(size_t)s.kpos + (size_t)(r - r0 - s.t0)] = val[k];
       }
     // give up early on matrices the sample misjudged
-    if (c.spmv_format < 0 && (b & 1023) == 1023 && (long long)(rb.seg.size() / 4) * 8 > (long long)ind[r1]) return PSP_OK;
+    if (!force && (b & 1023) == 1023 && (long long)(rb.seg.size() / 4) * 8 > (long long)ind[r1]) return false;
   }
-  if (c.spmv_format < 0 && (long long)(rb.seg.size() / 4) * 16 > nnz) return PSP_OK;     // mean run shorter than 16 rows
+  if (!force && (long long)(rb.seg.size() / 4) * 16 > nnz) return false;     // mean run shorter than 16 rows
+  return true;
+}
+
+int runs_try_csr(psp_mat *A, const int *ind, const int *col, const double *val, const int *gcol, int grow0,
+                 int own_cols, bool *accepted) {
+  *accepted = false;
+  Ctx &c = ctx();
+  if (c.spmv_format == 0) return PSP_OK;
+  if (c.spmv_format < 0 && !runs_pay_off(12LL * ind[A->m])) return PSP_OK;
+  RunBuild rb;
+  if (!build_csr_runs(A->m, ind, col, val, gcol, grow0, c.spmv_format > 0, rb)) return PSP_OK;
   PSP_TRY(upload_runs(A, rb, own_cols));
   *accepted = true;
   return PSP_OK;
 }
 
-int runs_try_sss(psp_mat *A, const int *ind, const int *col, const double *val, const double *diag, bool *accepted) {
-  *accepted = false;
-  Ctx &c = ctx();
-  const int n = A->n;
+static bool build_sss_runs(int n, const int *ind, const int *col, const double *val, const double *diag, bool force,
+                           RunBuild &rb) {
   const long long nnz = ind[n];
-  if (c.spmv_format == 0 || n == 0) return PSP_OK;
-  if (nnz > 0 && c.spmv_format < 0 && !sample_accepts(n, ind, col, nullptr, 0)) return PSP_OK;
-  if (nnz + n >= (1LL << 31)) return PSP_OK;
+  if (n == 0) return false;
+  if (nnz > 0 && !force && !sample_accepts(n, ind, col, nullptr, 0)) return false;
+  if (nnz + n >= (1LL << 31)) return false;
   const int nb = (n + kThreads - 1) / kThreads;
-  RunBuild rb;
   rb.val.resize((size_t)nnz + (size_t)n);
   std::copy(diag, diag + n, rb.val.begin() + nnz);
   struct Upper { int tb; Seg s; };
@@ -316,7 +327,7 @@ int runs_try_sss(psp_mat *A, const int *ind, const int *col, const double *val, 
       }
   }
   long long nseg = (long long)upper.size() * 2 + nb;
-  if (c.spmv_format < 0 && nnz > 0 && nseg * 16 > 2 * nnz + n) return PSP_OK;
+  if (!force && nnz > 0 && nseg * 16 > 2 * nnz + n) return false;
   // counting sort of the mirrored runs by target block, then by (diagonal, row) inside a block
   std::vector<int> start((size_t)nb + 1, 0);
   for (const Upper &u : upper) start[(size_t)u.tb + 1]++;
@@ -338,8 +349,18 @@ int runs_try_sss(psp_mat *A, const int *ind, const int *col, const double *val, 
     for (int i = start[(size_t)b]; i < start[(size_t)b + 1]; i++) emit(usorted[(size_t)i]);
     rb.blk[4 * (size_t)b + 3] = (int)(rb.seg.size() / 4);
   }
+  return true;
+}
+
+int runs_try_sss(psp_mat *A, const int *ind, const int *col, const double *val, const double *diag, bool *accepted) {
+  *accepted = false;
+  Ctx &c = ctx();
+  if (c.spmv_format == 0) return PSP_OK;
+  if (c.spmv_format < 0 && !runs_pay_off(12LL * (2LL * ind[A->n] + A->n))) return PSP_OK;
+  RunBuild rb;
+  if (!build_sss_runs(A->n, ind, col, val, diag, c.spmv_format > 0, rb)) return PSP_OK;
   PSP_TRY(upload_runs(A, rb, -1));
-  A->d_diag = A->d_rval + nnz;          // the SSOR sweeps read the diagonal from here
+  A->d_diag = A->d_rval + ind[A->n];    // the SSOR sweeps read the diagonal from here
   *accepted = true;
   return PSP_OK;
 }
@@ -371,3 +392,26 @@ int runs_to_csr(const psp_mat *A, std::vector<int> &ind, std::vector<int> &col, 
 }
 
 }  // namespace psp
+
+// ---------------------------------------------------------------- C-ABI: host-only analysis
+// The structure work of the format (bit-exact integer work, no GPU needed; used by the CPU tests).
+using namespace psp;
+
+extern "C" int psp_runs_analyze(int sss, int m, const int *ind, const int *col, const double *val, const double *diag,
+                                int *nblk, int *nseg, long long *nval, int **blk, int **seg, double **rval) {
+  if (!ind || !nblk || !nseg || !nval || !blk || !seg || !rval) { set_error("psp_runs_analyze: NULL argument"); return PSP_ERR_ARG; }
+  RunBuild rb;
+  const bool ok = sss ? build_sss_runs(m, ind, col, val, diag, true, rb) : build_csr_runs(m, ind, col, val, nullptr, 0, true, rb);
+  if (!ok) { *nblk = 0; *nseg = 0; *nval = 0; *blk = nullptr; *seg = nullptr; *rval = nullptr; return PSP_OK; }
+  *nblk = (int)(rb.blk.size() / 4); *nseg = (int)(rb.seg.size() / 4); *nval = (long long)rb.val.size();
+  *blk = (int *)malloc(sizeof(int) * (rb.blk.size() + 1));
+  *seg = (int *)malloc(sizeof(int) * (rb.seg.size() + 1));
+  *rval = (double *)malloc(sizeof(double) * (rb.val.size() + 1));
+  if (!*blk || !*seg || !*rval) { free(*blk); free(*seg); free(*rval); set_error("psp_runs_analyze: out of memory"); return PSP_ERR_NOMEM; }
+  memcpy(*blk, rb.blk.data(), sizeof(int) * rb.blk.size());
+  memcpy(*seg, rb.seg.data(), sizeof(int) * rb.seg.size());
+  memcpy(*rval, rb.val.data(), sizeof(double) * rb.val.size());
+  return PSP_OK;
+}
+
+extern "C" void psp_runs_free(void *p) { free(p); }

@@ -117,6 +117,8 @@ __device__ __forceinline__ void run_pass(const RunView &A, const double *x, RunS
         // (2) all loads, (3) the adds.  Nothing in (2) depends on a load in flight: a warp has six
         // scoreboards, and a descriptor read placed between the global loads ends up waiting
         // on a scoreboard it shares with them -- one DRAM round trip per run instead of per batch.
+        // (ptxas still forms the first product before the last loads are issued; forcing all
+        // loads first through an artificial data dependency measured slower, profiles/r2_runs_notes.md.)
         for (int s = 0; s < ns; s += UNROLL) {
           unsigned iv[UNROLL], ix[UNROLL];
           bool in[UNROLL];

@@ -13,12 +13,32 @@ void set_error(const char *fmt, ...) {
   va_end(ap);
 }
 
-Ctx &ctx() { return g_ctx; }
+static thread_local Ctx *t_ctx = nullptr;         // set in the worker threads of the multi-GPU layer
+Ctx &ctx() { return t_ctx ? *t_ctx : g_ctx; }
+void set_thread_ctx(Ctx *c) { t_ctx = c; }
 
 static int do_init(int device) {
   Ctx &c = g_ctx;
   if (c.ready && c.device == device) return PSP_OK;
   if (c.ready) { set_error("psp_init: already initialised on device %d", c.device); return PSP_ERR_ARG; }
+  PSP_TRY(init_ctx(c, device));
+  // PSP_OPTS="name=value,name=value": tuning knobs from the environment (see psp_set_option)
+  if (const char *opts = getenv("PSP_OPTS")) {
+    char buf[256];
+    strncpy(buf, opts, sizeof buf - 1);
+    buf[sizeof buf - 1] = 0;
+    for (char *tok = strtok(buf, ","); tok; tok = strtok(nullptr, ",")) {
+      char *eq = strchr(tok, '=');
+      if (!eq) continue;
+      *eq = 0;
+      psp_set_option(tok, atoll(eq + 1));
+    }
+  }
+  if (const char *g = getenv("PSP_GPUS")) psp_set_option("gpus", atoll(g));
+  return PSP_OK;
+}
+
+int init_ctx(Ctx &c, int device) {
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count == 0) {
@@ -50,22 +70,11 @@ static int do_init(int device) {
   PSP_CUDA(cudaEventCreateWithFlags(&c.evpoll[0], cudaEventDisableTiming));
   PSP_CUDA(cudaEventCreateWithFlags(&c.evpoll[1], cudaEventDisableTiming));
   c.ready = true;
-  // PSP_OPTS="name=value,name=value": tuning knobs from the environment (see psp_set_option)
-  if (const char *opts = getenv("PSP_OPTS")) {
-    char buf[256];
-    strncpy(buf, opts, sizeof buf - 1);
-    buf[sizeof buf - 1] = 0;
-    for (char *tok = strtok(buf, ","); tok; tok = strtok(nullptr, ",")) {
-      char *eq = strchr(tok, '=');
-      if (!eq) continue;
-      *eq = 0;
-      psp_set_option(tok, atoll(eq + 1));
-    }
-  }
   return PSP_OK;
 }
 
 int ensure_init() {
+  if (t_ctx) return PSP_OK;            // a rank thread: its context exists and its device is current
   if (g_ctx.ready) {
     cudaSetDevice(g_ctx.device);
     return PSP_OK;
@@ -77,7 +86,7 @@ int ensure_init() {
 }
 
 int ensure_stage(size_t elems) {
-  Ctx &c = g_ctx;
+  Ctx &c = ctx();
   if (c.stage_elems >= elems) return PSP_OK;
   if (c.stage) cudaFreeHost(c.stage);
   c.stage = nullptr; c.stage_elems = 0;
@@ -89,7 +98,7 @@ int ensure_stage(size_t elems) {
 }
 
 int pool_get(int slot, size_t elems, double **out) {
-  Ctx &c = g_ctx;
+  Ctx &c = ctx();
   if (elems == 0) elems = 1;
   if (c.pool_cap[slot] < elems || c.pool_cap[slot] > 4 * elems + (1u << 20)) {   // grow, or give back a much larger block
     if (c.pool[slot]) cudaFree(c.pool[slot]);
@@ -135,7 +144,7 @@ extern "C" long long psp_launch_count(int reset) {
 
 extern "C" int psp_synchronize(void) {
   PSP_TRY(ensure_init());
-  PSP_CUDA(cudaStreamSynchronize(g_ctx.stream));
+  PSP_CUDA(cudaStreamSynchronize(ctx().stream));
   return PSP_OK;
 }
 
@@ -172,7 +181,7 @@ extern "C" int psp_vec_upload(double *dptr, const double *host, size_t n, long i
   if (n == 0) return PSP_OK;
   if (!dptr || !host) { set_error("psp_vec_upload: NULL argument"); return PSP_ERR_ARG; }
   PSP_TRY(ensure_init());
-  Ctx &c = g_ctx;
+  Ctx &c = ctx();
   if (inc == 1) {
     PSP_CUDA(cudaMemcpyAsync(dptr, host, sizeof(double) * n, cudaMemcpyHostToDevice, c.stream));
     PSP_CUDA(cudaStreamSynchronize(c.stream));
@@ -189,7 +198,7 @@ extern "C" int psp_vec_download(const double *dptr, double *host, size_t n, long
   if (n == 0) return PSP_OK;
   if (!dptr || !host) { set_error("psp_vec_download: NULL argument"); return PSP_ERR_ARG; }
   PSP_TRY(ensure_init());
-  Ctx &c = g_ctx;
+  Ctx &c = ctx();
   if (inc == 1) {
     PSP_CUDA(cudaMemcpyAsync(host, dptr, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
     PSP_CUDA(cudaStreamSynchronize(c.stream));
@@ -205,7 +214,7 @@ extern "C" int psp_vec_download(const double *dptr, double *host, size_t n, long
 extern "C" int psp_vec_fill(double *dptr, size_t n, double value) {
   if (n == 0) return PSP_OK;
   PSP_TRY(ensure_init());
-  k_fill<<<grid_for(n), kThreads, 0, g_ctx.stream>>>(dptr, n, value);
+  k_fill<<<grid_for(n), kThreads, 0, ctx().stream>>>(dptr, n, value);
   PSP_LAUNCH_CHECK();
   return PSP_OK;
 }
@@ -254,6 +263,10 @@ extern "C" int psp_set_option(const char *name, long long value) {
   if (!strcmp(name, "spmv_variant")) c.spmv_variant = value;
   else if (!strcmp(name, "spmv_ctas")) c.spmv_ctas = value;
   else if (!strcmp(name, "spmv_format")) c.spmv_format = value;
+  else if (!strcmp(name, "gpus")) {
+    if (value < 1 || value > kMaxRanks) { set_error("gpus must be 1..%d", kMaxRanks); return PSP_ERR_ARG; }
+    c.gpus = value;
+  }
   else if (!strcmp(name, "poll_chunk")) c.poll_chunk = value;
   else if (!strcmp(name, "l2_stream")) c.l2_stream = value;
   else if (!strcmp(name, "pcg_persist")) c.pcg_persist = value;
@@ -273,6 +286,7 @@ extern "C" long long psp_get_option(const char *name) {
   if (!strcmp(name, "spmv_variant")) return c.spmv_variant;
   if (!strcmp(name, "spmv_ctas")) return c.spmv_ctas;
   if (!strcmp(name, "spmv_format")) return c.spmv_format;
+  if (!strcmp(name, "gpus")) return c.gpus;
   if (!strcmp(name, "poll_chunk")) return c.poll_chunk;
   if (!strcmp(name, "sms")) return c.sms;
   if (!strcmp(name, "l2_stream")) return c.l2_stream;

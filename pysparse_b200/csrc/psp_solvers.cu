@@ -803,10 +803,21 @@ struct SolveFrame {
 static int solve_dev_frame(int solver, const psp_operator *Aop, const psp_operator *Kop, int n, const double *db,
                            double *dx, double tol, int maxit, int gmres_dim, int *info, int *iter, double *relres);
 
+// gpus > 1 and the operands allow it: the sharded solve on all GPUs (psp_multi.cu)
+static bool wants_multi(int solver, const psp_operator *Aop, const psp_operator *Kop, int n) {
+  if (!Aop || !Aop->mat || ctx().solve_depth != 0 || Aop->mat->n != n) return false;
+  const bool kp = Kop && (Kop->mat || Kop->prec || Kop->cb);
+  return multi_eligible(solver, Aop->mat, Kop ? Kop->prec : nullptr, kp);
+}
+
 int solve_dev(int solver, const psp_operator *Aop, const psp_operator *Kop, int n, const double *db,
               double *dx, double tol, int maxit, int gmres_dim, int *info, int *iter, double *relres) {
   PSP_TRY(ensure_init());
   Ctx &c = ctx();
+  if (wants_multi(solver, Aop, Kop, n)) {
+    PSP_CUDA(cudaStreamSynchronize(c.stream));      // b and x are complete before the other devices read them
+    return multi_solve(solver, Aop->mat, Kop ? Kop->prec : nullptr, db, dx, true, tol, maxit, gmres_dim, info, iter, relres);
+  }
   if (c.solve_depth == 0) {
     c.solve_depth = 1;
     const int st = solve_dev_frame(solver, Aop, Kop, n, db, dx, tol, maxit, gmres_dim, info, iter, relres);
@@ -989,6 +1000,8 @@ extern "C" int psp_solve(int solver, const psp_operator *A, const psp_operator *
                          int *info, int *iter, double *relres) {
   if (n < 0 || (n > 0 && (!b || !x))) { set_error("psp_solve: NULL vector"); return PSP_ERR_ARG; }
   PSP_TRY(ensure_init());
+  if (wants_multi(solver, A, K, n))                 // every GPU takes its slices straight from the host arrays
+    return multi_solve(solver, A->mat, K ? K->prec : nullptr, b, x, false, tol, maxit, gmres_dim, info, iter, relres);
   double *db = nullptr, *dx = nullptr;
   const bool pooled = (ctx().solve_depth == 0);
   if (pooled) {

@@ -218,7 +218,8 @@ __global__ void __launch_bounds__(kThreads) k_spmv_tma(SpmvArgs a) {
 template <int STAGES, bool DOTS>
 static int launch_tma(const SpmvArgs &a, int nb, int ctas_per_sm) {
   Ctx &c = ctx();
-  static int resident = 0, cached_cap = -1;
+  static_assert(STAGES == 2 || STAGES == 3, "launch cache is indexed by STAGES - 2");
+  int &resident = c.occ_tma[STAGES - 2][DOTS ? 1 : 0], &cached_cap = c.occ_tma_cap[STAGES - 2][DOTS ? 1 : 0];
   const int smem_bytes = STAGES * kStageBytes;
   if (resident == 0 || cached_cap != ctas_per_sm) {
     cached_cap = ctas_per_sm;
@@ -353,6 +354,28 @@ int csr_create(int m, int n, long long nnz, const int *ind, const int *col, cons
   return PSP_OK;
 }
 
+// symmetric expansion of an SSS matrix in to_csr() order (ll_mat.c:1601-1623)
+void sss_expand(int n, long long nnz, const int *ind, const int *col, const double *val, const double *diag,
+                std::vector<int> &find, std::vector<int> &fcol, std::vector<double> &fval) {
+  const long long fnnz = 2 * nnz + n;
+  find.assign((size_t)n + 1, 0); fcol.resize((size_t)fnnz); fval.resize((size_t)fnnz);
+  std::vector<int> fill((size_t)(n > 0 ? n : 1));
+  for (int i = 0; i < n; i++) find[i + 1] = ind[i + 1] - ind[i] + 1;
+  for (long long k = 0; k < nnz; k++) find[col[k] + 1]++;
+  for (int i = 0; i < n; i++) find[i + 1] += find[i];
+  for (int i = 0; i < n; i++) {
+    int p = find[i];
+    for (int k = ind[i]; k < ind[i + 1]; k++) { fcol[p] = col[k]; fval[p] = val[k]; p++; }
+    fcol[p] = i; fval[p] = diag[i]; p++;
+    fill[i] = p;
+  }
+  for (int i = 0; i < n; i++)               // rows ascending => upper parts ascending
+    for (int k = ind[i]; k < ind[i + 1]; k++) {
+      int j = col[k];
+      fcol[fill[j]] = i; fval[fill[j]] = val[k]; fill[j]++;
+    }
+}
+
 int sss_create(int n, long long nnz, const int *ind, const int *col, const double *val,
                const double *diag, psp_mat **out) {
   PSP_TRY(check_csr(n, n, nnz, ind, col, true));
@@ -376,23 +399,9 @@ int sss_create(int n, long long nnz, const int *ind, const int *col, const doubl
   }
   // irregular symmetric matrices: fall back to the one-time symmetric expansion
   if (fnnz >= (1LL << 31)) { psp_mat_destroy(A); set_error("expanded SSS matrix exceeds 2^31 entries"); return PSP_ERR_ARG; }
-  // symmetric expansion in to_csr() order (ll_mat.c:1601-1623)
-  std::vector<int> find((size_t)n + 1, 0), fcol((size_t)fnnz), fill((size_t)n);
-  std::vector<double> fval((size_t)fnnz);
-  for (int i = 0; i < n; i++) find[i + 1] = ind[i + 1] - ind[i] + 1;
-  for (long long k = 0; k < nnz; k++) find[col[k] + 1]++;
-  for (int i = 0; i < n; i++) find[i + 1] += find[i];
-  for (int i = 0; i < n; i++) {
-    int p = find[i];
-    for (int k = ind[i]; k < ind[i + 1]; k++) { fcol[p] = col[k]; fval[p] = val[k]; p++; }
-    fcol[p] = i; fval[p] = diag[i]; p++;
-    fill[i] = p;
-  }
-  for (int i = 0; i < n; i++)               // rows ascending => upper parts ascending
-    for (int k = ind[i]; k < ind[i + 1]; k++) {
-      int j = col[k];
-      fcol[fill[j]] = i; fval[fill[j]] = val[k]; fill[j]++;
-    }
+  std::vector<int> find, fcol;
+  std::vector<double> fval;
+  sss_expand(n, nnz, ind, col, val, diag, find, fcol, fval);
   int st = finish_csr_upload(A, find, fcol.data(), fval.data());
   if (st == PSP_OK) st = upload(diag, sizeof(double) * (size_t)n, (void **)&A->d_diag);
   if (st == PSP_OK && cudaStreamSynchronize(ctx().stream) != cudaSuccess) st = PSP_ERR_CUDA;
@@ -483,8 +492,7 @@ static int spmv_dispatch(const psp_mat *A, const double *dx, double *dy, const S
   }
   const bool vec = (c.spmv_variant != 1);
   // persistent grid: exactly the number of CTAs that are resident at once
-  static int resident[2][2] = {{0, 0}, {0, 0}};
-  int &res = resident[vec ? 1 : 0][d.S ? 1 : 0];
+  int &res = c.occ_stream[vec ? 1 : 0][d.S ? 1 : 0];
   if (res == 0) {
     const void *fn = vec ? (d.S ? (const void *)k_spmv_stream<1, true> : (const void *)k_spmv_stream<1, false>)
                          : (d.S ? (const void *)k_spmv_stream<0, true> : (const void *)k_spmv_stream<0, false>);
@@ -520,7 +528,12 @@ extern "C" int psp_csr_create(int m, int n, int nnz, const int *ind, const int *
                               const double *val, psp_mat **out) {
   if (!out || !ind || (nnz > 0 && (!col || !val))) { set_error("psp_csr_create: NULL argument"); return PSP_ERR_ARG; }
   PSP_TRY(ensure_init());
-  return csr_create(m, n, nnz, ind, col, val, out, false, -1, nullptr, 0);
+  PSP_TRY(csr_create(m, n, nnz, ind, col, val, out, false, -1, nullptr, 0));
+  if (multi_gpus() > 1) {                // additionally: row slabs on the other GPUs (psp_multi.cu)
+    int st = multi_attach_csr(*out, ind, col, val);
+    if (st != PSP_OK) { psp_mat_destroy(*out); *out = nullptr; return st; }
+  }
+  return PSP_OK;
 }
 
 extern "C" int psp_sss_create(int n, int nnz, const int *ind, const int *col, const double *val,
@@ -530,11 +543,22 @@ extern "C" int psp_sss_create(int n, int nnz, const int *ind, const int *col, co
     return PSP_ERR_ARG;
   }
   PSP_TRY(ensure_init());
-  return sss_create(n, nnz, ind, col, val, diag, out);
+  PSP_TRY(sss_create(n, nnz, ind, col, val, diag, out));
+  if (multi_gpus() > 1 && 2LL * nnz + n < (1LL << 31)) {
+    // sharded form: rows of the symmetric expansion (every slab gathers over its own rows, the
+    // entries of the lower triangle it needs from later rows are replicated into it)
+    std::vector<int> find, fcol;
+    std::vector<double> fval;
+    sss_expand(n, nnz, ind, col, val, diag, find, fcol, fval);
+    int st = multi_attach_csr(*out, find.data(), fcol.data(), fval.data());
+    if (st != PSP_OK) { psp_mat_destroy(*out); *out = nullptr; return st; }
+  }
+  return PSP_OK;
 }
 
 extern "C" void psp_mat_destroy(psp_mat *A) {
   if (!A) return;
+  if (A->multi) { multi_detach(A->multi); A->multi = nullptr; }
   if (A->transp) psp_mat_destroy(A->transp);
   cudaFree(A->d_ind); cudaFree(A->d_col); cudaFree(A->d_val); cudaFree(A->d_blk); cudaFree(A->d_blk_halo);
   if (!(A->fmt == 1 && A->kind == 2)) cudaFree(A->d_diag);      // run format: the diagonal lives inside d_rval

@@ -12,5 +12,5 @@ run() {  # tool, name, kernels...
 }
 run memcheck all spmv pcg ssor phase
 run racecheck spmv_pcg spmv pcg
-run racecheck ssor ssor
+run racecheck ssor ssor      # the point-to-point engine synchronises two warps through volatile shared-memory words on purpose: expect "hazards" there
 run synccheck all spmv pcg ssor

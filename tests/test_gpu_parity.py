@@ -83,11 +83,11 @@ def test_spmv_strided_views(gpu, checker):
     assert np.array_equal(ys, yo)
 
 
-@pytest.fixture(params=["auto", "rowblocks"])
+@pytest.fixture(params=["runs", "rowblocks"])
 def device_format(request, native):
-    """Both device layouts of a matrix: what the analysis picks (diagonal runs for every stencil
-    matrix of the suite) and the CSR row-block stream forced."""
-    native.set_option("spmv_format", -1 if request.param == "auto" else 0)
+    """Both device layouts of a matrix, forced: diagonal runs (the automatic choice for matrices
+    of a gigabyte and more) and the CSR row-block stream (the automatic choice below that)."""
+    native.set_option("spmv_format", 1 if request.param == "runs" else 0)
     yield request.param
     native.set_option("spmv_format", -1)
 
