@@ -145,8 +145,12 @@ struct Ctx {
   long long pcg_persist = -1; // single-launch PCG: 1 always, 0 never, -1 automatic
   long long ssor_engine = 0;  // SSOR sweeps: 0 automatic, 1 grid-wide barrier, 2 cluster barrier, 3 single CTA, 4 point-to-point (read when the preconditioner is created)
   long long ssor_cluster = 8; // CTAs in the sweep cluster (8 portable, 16 non-portable)
-  long long gmres_persist = 0; // 1: single-launch GMRES kernel (psp_persist_gmres.cu; not yet validated on a GPU)
-  long long bicg_persist = 0; // 1: single-launch BiCGSTAB kernel (psp_persist_bicg.cu; not yet validated on a GPU)
+  // single-launch kernels of the other two sharded solvers: 1 always, 0 never, -1 automatic.
+  // Measured on conv-diff 200^3 (it/s, per-phase vs single launch, 1/2/4/8 GPUs): BiCGSTAB
+  // 1757/2819/4471/6680 vs 1771/3190/5765/10733 -> always; GMRES(30) 937/1567/2292/2638 vs
+  // 762/1447/2771/3712 -> from 4 GPUs on (profiles/r2_multi_notes.md)
+  long long gmres_persist = -1;
+  long long bicg_persist = -1;
   long long dist_push = 1;    // sharded single-launch PCG: push the halo to the neighbours (needs the send map)
   long long dist_debug = 0;   // timing diagnostics only (results invalid): 1 skip halo pull, 2 also skip the cross-GPU all-reduce
   long long poll_chunk = 0;   // 0: automatic

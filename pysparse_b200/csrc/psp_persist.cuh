@@ -25,6 +25,13 @@ namespace psp {
 #ifndef PSP_VEC_UNROLL
 #define PSP_VEC_UNROLL 1
 #endif
+// Halo unpack of the sharded single-launch PCG: block-local by default (every boundary row block
+// copies the landing-zone words it needs right before it is multiplied; no unpack pass, no
+// tickets): 83.0 -> 80.5 us per iteration on 8 GPUs, 163 -> 159 on 4 (profiles/r2_multi_notes.md).
+// -DPSP_NO_BLOCK_UNPACK restores the separate unpack pass.
+#if !defined(PSP_NO_BLOCK_UNPACK) && !defined(PSP_BLOCK_UNPACK)
+#define PSP_BLOCK_UNPACK 1
+#endif
 constexpr int kPersistStages = PSP_PERSIST_STAGES;   // TMA ring depth
 constexpr int kPersistCtas = PSP_PERSIST_CTAS;       // CTAs per SM the register budget is sized for
 constexpr int kVecUnroll = PSP_VEC_UNROLL;           // elements per thread and trip in the vector phases

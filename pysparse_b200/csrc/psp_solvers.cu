@@ -512,10 +512,10 @@ static int solve_bicgstab(Solve &s, const double *b, double *x, double *work) {
   double *phat = ident ? p : phatb, *shat = ident ? sv : shatb;
   const int pub = s.dm ? kPublish : 0;     // multi-GPU: phat / shat are read by the neighbours
   {
-    // single-launch path (psp_persist_bicg.cu): opt-in until it has been validated on a GPU
+    // single-launch path (psp_persist_bicg.cu): the default whenever operator and preconditioner are native
     Ctx &c = ctx();
     const psp_mat *M = s.dm ? s.dm->local : s.A.mat;
-    if (M && s.fusedK && c.bicg_persist == 1) {
+    if (M && s.fusedK && c.bicg_persist != 0) {
       double *p2 = (s.dm && dist().nslots >= 9) ? work + 8 * vs : nullptr;   // second p buffer (push model)
       return bicg_persist_launch(M, (int)n, b, x, r, rhat, p, p2, phat, v, sv, shat, t, s.dinv, s.dm);
     }
@@ -743,9 +743,11 @@ static int solve_gmres(Solve &s, const double *b, double *x, int m) {
     return PSP_OK;
   };
   {
-    // single-launch path (psp_persist_gmres.cu): opt-in until it has been validated on a GPU
+    // single-launch path (psp_persist_gmres.cu): pays off when the launches and all-reduces of a
+    // restart cycle cross several GPUs (automatic from 4 ranks on)
     const psp_mat *M = s.dm ? s.dm->local : s.A.mat;
-    if (M && s.fusedK && c.gmres_persist == 1 && m <= 256) {
+    const bool want = c.gmres_persist == 1 || (c.gmres_persist < 0 && s.dm && dist().world >= 4);
+    if (M && s.fusedK && want && m <= 256) {
       st = gmres_persist_launch(M, (int)n, b, x, V, W, s.dm ? xs : x, N, m, s.dinv, G.g, s.dm);
       cudaStreamSynchronize(c.stream);
       cleanup();

@@ -34,7 +34,7 @@ if "pcg" in which:
     P.set_option("bicg_persist", 1)
     xs = np.zeros(n)
     print("bicgstab single launch", P.solve("bicgstab", A, np.ones(n), xs, 1e-8, 40, P.Precon.jacobi(None, np.full(n, 6.0))), flush=True)
-    P.set_option("bicg_persist", 0)
+    P.set_option("bicg_persist", -1)
     P.set_option("pcg_persist", -1)
 if "ssor" in which:
     m2 = g.poisson2d(24)

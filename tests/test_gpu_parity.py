@@ -257,9 +257,10 @@ BICG_CASES = [c for c in SOLVER_CASES if c["solver"] == "bicgstab" and c.get("pr
 
 @pytest.mark.parametrize("case", BICG_CASES, ids=lambda c: c["id"])
 def test_bicgstab_single_launch_kernel_vs_per_phase_kernels(gpu, native, case, device_format):
-    """k_bicgstab_persist (option bicg_persist = 1; the per-phase sequence stays the single-GPU
-    default because it is faster there, profiles/r2_persist_notes.md) runs the same arithmetic
-    in the same order as the per-phase kernels: identical flag, count, residual and iterate."""
+    """k_bicgstab_persist (the default; bicg_persist = 0 selects the per-phase kernel sequence)
+    runs the same algorithm as the per-phase kernels: same flag, iteration count within the
+    contract, same residual and iterate to solver accuracy (the order of the partial sums of the
+    dot products differs between the two, so the last bits do)."""
     mat = build_matrix(case["matrix"])
     n = mat["n"]
     out = []
@@ -272,11 +273,44 @@ def test_bicgstab_single_launch_kernel_vs_per_phase_kernels(gpu, native, case, d
             r = gpu.solve("bicgstab", A, b, x, case["tol"], case["maxit"], K)
             out.append((r, x.copy(), native.launch_count()))
         finally:
-            native.set_option("bicg_persist", 0)
+            native.set_option("bicg_persist", -1)
     (r0, x0, l0), (r1, x1, l1) = out
     assert l1 == 1 and l0 > 1
-    assert r0[:2] == r1[:2] and (r0[2] == r1[2] or (np.isnan(r0[2]) and np.isnan(r1[2]))), (r0, r1)
-    assert np.array_equal(x0, x1)
+    tol_it = ITER_TOL if case.get("stable", False) else 0.35     # Poisson cases: rounding-chaotic (parity)
+    assert r0[0] == r1[0] and abs(r0[1] - r1[1]) <= max(1, int(tol_it * r0[1])), (r0, r1)
+    if np.isfinite(r0[2]) and r0[0] == 0:
+        assert r1[2] < case["tol"]
+    scale = max(1.0, float(np.max(np.abs(x0))))
+    assert float(np.max(np.abs(x0 - x1))) <= 50 * case["tol"] * scale * max(1.0, n ** 0.5) + 1e-9 * scale
+
+
+GMRES_CASES = [c for c in SOLVER_CASES if c["solver"] == "gmres" and c.get("prec") in (None, "jacobi") and c.get("steps", 1) == 1]
+
+
+@pytest.mark.parametrize("case", GMRES_CASES, ids=lambda c: c["id"])
+def test_gmres_single_launch_kernel_vs_per_phase_kernels(gpu, native, case, device_format):
+    """k_gmres_persist (gmres_persist = 1; chosen automatically from 4 GPUs on) against the
+    per-phase kernel sequence: same flag and restart-cycle structure, iteration count within
+    the contract, same true-residual relres and iterate."""
+    mat = build_matrix(case["matrix"])
+    n = mat["n"]
+    out = []
+    for persist in (0, 1):
+        native.set_option("gmres_persist", persist)
+        try:
+            A, K = make_ops(gpu, mat, case)
+            b, x = start_vectors(case, n)
+            native.launch_count(reset=True)
+            r = gpu.solve("gmres", A, b, x, case["tol"], case["maxit"], K, case.get("dim", 20))
+            out.append((r, x.copy(), native.launch_count()))
+        finally:
+            native.set_option("gmres_persist", -1)
+    (r0, x0, l0), (r1, x1, l1) = out
+    assert l1 == 1 and l0 > 1
+    assert r0[0] == r1[0] and abs(r0[1] - r1[1]) <= max(1, int(ITER_TOL * r0[1])), (r0, r1)
+    assert abs(r0[2] - r1[2]) <= max(RELRES_TOL, 1e-6 * abs(r0[2])), (r0, r1)
+    scale = max(1.0, float(np.max(np.abs(x0))))
+    assert float(np.max(np.abs(x0 - x1))) <= 50 * case["tol"] * scale * max(1.0, n ** 0.5) + 1e-9 * scale
 
 
 @pytest.mark.parametrize("matrix", [["poisson2d", 40], ["random_sym", 3000, 7, 4], ["poisson3d", 12]],
@@ -311,6 +345,18 @@ def test_options_round_trip(native):
         native.set_option(name, old)
     with pytest.raises(Exception):
         native.set_option("no_such_option", 1)
+
+
+def test_plugin_api_drives_two_gpus_from_one_process(native):
+    """PSP_GPUS=2: krylov.pcg / bicgstab / gmres on sss_mat / csr_mat objects run sharded over two
+    GPUs from this one process and agree with the one-GPU solve (scripts/multi_check.py).
+    Needs two GPUs."""
+    import os, subprocess, sys
+    if native.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "scripts", "multi_check.py"), "2"], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and "MULTI CHECK PASSED" in p.stdout, p.stdout[-3000:] + p.stderr[-2000:]
 
 
 def test_sharded_solvers_two_gpus(native):

@@ -6,7 +6,7 @@ run_epilogue() / State (compiled from pysparse_b200/csrc/psp_epilogue.cuh) -- he
 run against the oracle: same flag, iterations within 2 %, residual and solution to tolerance.
 The PCG flow belongs to a kernel that is validated on the GPU, so it also validates the
 method; the BiCGSTAB and GMRES flows belong to kernels written at the end of round 1 that
-have not been run on a GPU yet (they are opt-in: bicg_persist / gmres_persist)."""
+are checked on the GPU as well (tests/test_gpu_parity.py); this is the CPU-only check of their control flow."""
 import ctypes as C
 import os
 import subprocess
