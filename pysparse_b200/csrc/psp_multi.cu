@@ -8,7 +8,7 @@
 //     and upload slab r to device r (psp_dist.cu: local column numbering, halo tables, send
 //     maps -- the same structures the one-process-per-GPU launcher builds);
 //   * psp_solve / psp_solve_dev scatter b and x to the devices, run the sharded solver
-//     (psp_solvers.cu: dist_solve_dev; PCG, BiCGSTAB, GMRES with no or single-step Jacobi
+//     (psp_solvers.cu: dist_solve_dev; all six solvers, with no or single-step Jacobi
 //     preconditioning) on all of them at once and gather x.
 // One host thread per GPU ("rank thread") owns that device's context, stream and slab and
 // launches its persistent solver kernel; the kernels talk to each other directly over NVLink
@@ -234,7 +234,7 @@ void multi_prec_release(psp_prec *K) {
 
 bool multi_eligible(int solver, const psp_mat *A, const psp_prec *K, bool K_present) {
   if (!A || !A->multi) return false;
-  if (solver != PSP_PCG && solver != PSP_BICGSTAB && solver != PSP_GMRES) return false;
+  if (solver < PSP_PCG || solver > PSP_GMRES) return false;
   if (!K_present) return true;
   return K && K->kind == 1 && K->steps == 1 && (int)K->h_dinv.size() == A->n;
 }
@@ -246,7 +246,8 @@ int multi_solve(int solver, psp_mat *A, psp_prec *K, const double *b, double *x,
   const int world = mm->world;
   Ctx &main = ctx();
   if (solver == PSP_GMRES && gmres_dim < 1) { set_error("gmres: dim must be >= 1"); return PSP_ERR_ARG; }
-  const int slots = solver == PSP_PCG ? 4 : (solver == PSP_BICGSTAB ? 9 : (K ? 2 * gmres_dim + 2 : gmres_dim + 2));
+  const int slots = solver == PSP_PCG ? 4 : solver == PSP_BICGSTAB ? 9 : solver == PSP_MINRES ? 7 : solver == PSP_QMRS ? 6
+                  : solver == PSP_CGS ? 9 : (K ? 2 * gmres_dim + 2 : gmres_dim + 2);
   PSP_TRY(ensure_heap((size_t)mm->max_slot + 64, slots));
   PSP_TRY(bind_sendmaps(mm));
   for (Rank *r : M.ranks) copy_options(r->ctx, main);

@@ -338,10 +338,16 @@ struct FMinresUpdate {      // w, w_old, x update (minres.c:176-184) + loop test
 
 static int solve_minres(Solve &s, const double *b, double *x, double *work) {
   const long n = s.n;
-  double *vh_old = work, *vh = work + n, *ybuf = work + 2 * n, *w = work + 3 * n,
-         *w_old = work + 4 * n, *v = work + 5 * n, *av = work + 6 * n;
+  const long vs = s.vstride ? s.vstride : n;
+  double *vh_old = work, *vh = work + vs, *ybuf = work + 2 * vs, *w = work + 3 * vs,
+         *w_old = work + 4 * vs, *v = work + 5 * vs, *av = work + 6 * vs;
+  const int pub = s.dm ? kPublish : 0;     // multi-GPU: v is read by the neighbours
   // identity preconditioner: y is vh itself (never written separately)
   double *y = (s.fusedK && !s.dinv) ? vh : ybuf;
+  if (s.dm) {
+    PSP_TRY(launch_map(FCopy{x, v}, n, EPI_NONE, pub));   // x0 into the shared heap, published
+    PSP_TRY(apply_A(s, v, vh));
+  } else
   PSP_TRY(apply_A(s, x, vh));
   PSP_TRY(launch_map(FMinresInit{b, vh, vh_old, w, w_old}, n, EPI_MINRES_R0));
   if (s.fusedK) {
@@ -350,9 +356,9 @@ static int solve_minres(Solve &s, const double *b, double *x, double *work) {
     PSP_TRY(apply_K(s, vh, y));
     PSP_TRY(launch_map(FDot{vh, y}, n, EPI_MINRES_BETA0));
   }
-  const bool sync_each = !(s.A.mat && (s.fusedK || s.K.prec));
+  const bool sync_each = !((s.A.mat || s.dm) && (s.fusedK || s.K.prec));
   auto body = [&](long long) -> int {
-    PSP_TRY(launch_map(FMinresV{y, v, 0.0}, n));
+    PSP_TRY(launch_map(FMinresV{y, v, 0.0}, n, EPI_NONE, pub));
     PSP_TRY(apply_A(s, v, av, v, nullptr, false, EPI_MINRES_ALPHA));
     if (s.fusedK) {
       PSP_TRY(launch_map(FMinresLanczos<true>{av, s.dinv, vh, vh_old, y, 0.0, 0.0}, n, EPI_MINRES_BETA));
@@ -417,19 +423,21 @@ struct FQmrsUpdate {        // d = p eta + d cc ; x += d ; v *= 1/rho1   (qmrs.c
 
 static int solve_qmrs(Solve &s, const double *b, double *x, double *work) {
   const long n = s.n;
-  double *t0 = work, *p = work + n, *d = work + 2 * n, *v = work + 3 * n, *t = work + 4 * n,
-         *g = work + 5 * n;
+  const long vs = s.vstride ? s.vstride : n;
+  double *t0 = work, *p = work + vs, *d = work + 2 * vs, *v = work + 3 * vs, *t = work + 4 * vs,
+         *g = work + 5 * vs;
+  const int pub = s.dm ? kPublish : 0;     // multi-GPU: g is read by the neighbours
   PSP_TRY(launch_map(FQmrsInit0{b, v}, n, EPI_QMRS_RHO0));
   PSP_TRY(launch_map(FQmrsInit1{v, p, g, d, x, 0.0}, n, EPI_QMRS_LOOP));
-  const bool sync_each = !(s.A.mat && (s.fusedK || s.K.prec));
+  const bool sync_each = !((s.A.mat || s.dm) && (s.fusedK || s.K.prec));
   auto body = [&](long long) -> int {
     if (s.fusedK) {
       PSP_TRY(launch_map(FDotK{v, s.dinv, nullptr}, n, EPI_QMRS_DELTA));
-      PSP_TRY(launch_map(FQmrsPG{v, nullptr, s.dinv, p, g, 0.0}, n));
+      PSP_TRY(launch_map(FQmrsPG{v, nullptr, s.dinv, p, g, 0.0}, n, EPI_NONE, pub));
     } else {
       PSP_TRY(apply_K(s, v, t0));
       PSP_TRY(launch_map(FDot{t0, v}, n, EPI_QMRS_DELTA));
-      PSP_TRY(launch_map(FQmrsPG{v, t0, nullptr, p, g, 0.0}, n));
+      PSP_TRY(launch_map(FQmrsPG{v, t0, nullptr, p, g, 0.0}, n, EPI_NONE, pub));
     }
     PSP_TRY(apply_A(s, g, t, g, nullptr, false, EPI_QMRS_EPS));
     PSP_TRY(launch_map(FQmrsV{t, v, 0.0}, n, EPI_QMRS_RHO1));
@@ -595,26 +603,33 @@ struct FCgsUP {             // u = r + beta q ; p = u + beta (q + beta p)   (cgs
 
 static int solve_cgs(Solve &s, const double *b, double *x, double *work) {
   const long n = s.n;
-  double *r0 = work, *r = work + n, *p = work + 2 * n, *q = work + 3 * n, *u = work + 4 * n,
-         *v = work + 5 * n, *ta = work + 6 * n, *tbb = work + 7 * n, *tc = work + 8 * n;
+  const long vs = s.vstride ? s.vstride : n;
+  double *r0 = work, *r = work + vs, *p = work + 2 * vs, *q = work + 3 * vs, *u = work + 4 * vs,
+         *v = work + 5 * vs, *ta = work + 6 * vs, *tbb = work + 7 * vs, *tc = work + 8 * vs;
   const bool ident = s.fusedK && !s.dinv;
+  // multi-GPU: the vectors A is applied to (K^-1 p and K^-1 (u + q)) are read by the neighbours
+  const int pub = s.dm ? kPublish : 0;
+  if (s.dm) {
+    PSP_TRY(launch_map(FCopy{x, tc}, n, EPI_NONE, pub));   // x0 into the shared heap, published
+    PSP_TRY(apply_A(s, tc, ta));
+  } else
   PSP_TRY(apply_A(s, x, ta));
-  PSP_TRY(launch_map(FCgsInit{b, ta, r0, r, u, p}, n, EPI_CGS_INIT));
-  const bool sync_each = !(s.A.mat && (s.fusedK || s.K.prec));
+  PSP_TRY(launch_map(FCgsInit{b, ta, r0, r, u, p}, n, EPI_CGS_INIT, ident ? pub : 0));   // identity K: p itself is multiplied next
+  const bool sync_each = !((s.A.mat || s.dm) && (s.fusedK || s.K.prec));
   auto body = [&](long long) -> int {
     const double *kp = p;                       // K^-1 p
     if (s.fusedK) {
-      if (s.dinv) { PSP_TRY(launch_map(FScaleBy{p, s.dinv, ta}, n)); kp = ta; }
+      if (s.dinv) { PSP_TRY(launch_map(FScaleBy{p, s.dinv, ta}, n, EPI_NONE, pub)); kp = ta; }
     } else {
       PSP_TRY(apply_K(s, p, ta)); kp = ta;
     }
     PSP_TRY(apply_A(s, kp, v, r0, nullptr, false, EPI_CGS_ALPHA));
     double *tb = ident ? ta : tbb;
-    PSP_TRY(launch_map(FCgsQ{u, v, s.fusedK ? s.dinv : nullptr, q, ta, tb, 0}, n));
+    PSP_TRY(launch_map(FCgsQ{u, v, s.fusedK ? s.dinv : nullptr, q, ta, tb, 0}, n, EPI_NONE, pub));
     if (!s.fusedK) PSP_TRY(apply_K(s, ta, tb));
     PSP_TRY(apply_A(s, tb, tc));
     PSP_TRY(launch_map(FCgsUpdate{tb, tc, r0, x, r, 0}, n, EPI_CGS_RES));
-    PSP_TRY(launch_map(FCgsUP{r, q, u, p, 0}, n, EPI_CGS_LOOP));
+    PSP_TRY(launch_map(FCgsUP{r, q, u, p, 0}, n, EPI_CGS_LOOP, ident ? pub : 0));
     return PSP_OK;
   };
   return run_until_done(s, (long long)ctx().h_state[0].maxit + 1, sync_each, body);
@@ -934,16 +949,14 @@ int dist_solve_dev(int solver, DistMat *dm, psp_prec *K, const double *db, doubl
   Ctx &c = ctx();
   DistHost &d = dist();
   if (!d.ready || !dm) { set_error("psp_dist_solve_dev: distributed layer not initialised"); return PSP_ERR_DIST; }
-  if (solver != PSP_PCG && solver != PSP_BICGSTAB && solver != PSP_GMRES) {
-    set_error("psp_dist_solve_dev: pcg, bicgstab and gmres are sharded in this release");
-    return PSP_ERR_ARG;
-  }
+  if (solver < PSP_PCG || solver > PSP_GMRES) { set_error("psp_dist_solve_dev: unknown solver id %d", solver); return PSP_ERR_ARG; }
   if (solver == PSP_GMRES && gmres_dim < 1) { set_error("gmres: dim must be >= 1"); return PSP_ERR_ARG; }
   if (K && !(K->kind == 1 && K->steps == 1 && K->n == dm->nl)) {
     set_error("psp_dist_solve_dev: preconditioner must be None or single-step Jacobi on the local rows");
     return PSP_ERR_ARG;
   }
-  const int need_slots = solver == PSP_PCG ? 4 : (solver == PSP_BICGSTAB ? 8 : 0);
+  const int need_slots = solver == PSP_PCG ? 4 : solver == PSP_BICGSTAB ? 8 : solver == PSP_MINRES ? 7 : solver == PSP_QMRS ? 6
+                       : solver == PSP_CGS ? 9 : 0;
   if (d.nslots < need_slots) {
     set_error("psp_dist_solve_dev: symmetric heap has %d slots, the solver needs %d", d.nslots, need_slots);
     return PSP_ERR_ARG;
@@ -967,7 +980,10 @@ int dist_solve_dev(int solver, DistMat *dm, psp_prec *K, const double *db, doubl
   PSP_CUDA(cudaStreamSynchronize(c.stream));
   PSP_CUDA(cudaEventRecord(c.ev0, c.stream));
   int st = solver == PSP_PCG ? solve_pcg(s, db, dx, d.heap)
-         : solver == PSP_BICGSTAB ? solve_bicgstab(s, db, dx, d.heap) : solve_gmres(s, db, dx, gmres_dim);
+         : solver == PSP_BICGSTAB ? solve_bicgstab(s, db, dx, d.heap)
+         : solver == PSP_MINRES ? solve_minres(s, db, dx, d.heap)
+         : solver == PSP_QMRS ? solve_qmrs(s, db, dx, d.heap)
+         : solver == PSP_CGS ? solve_cgs(s, db, dx, d.heap) : solve_gmres(s, db, dx, gmres_dim);
   if (st != PSP_OK) { cudaStreamSynchronize(c.stream); return st; }
   PSP_CUDA(cudaEventRecord(c.ev1, c.stream));
   PSP_CUDA(cudaMemcpyAsync(&c.h_state[0], c.state, sizeof(State), cudaMemcpyDeviceToHost, c.stream));

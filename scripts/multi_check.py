@@ -1,5 +1,5 @@
 """N GPUs behind the unchanged single-process API (PSP_GPUS / option "gpus"): parity of the
-sharded krylov.pcg / bicgstab / gmres against the one-GPU solve and the oracle, then timings.
+sharded krylov.pcg / minres / qmrs / bicgstab / cgs / gmres against the one-GPU solve and the oracle, then timings.
     python scripts/multi_check.py N [--time] [grid]"""
 import os, sys, time
 import numpy as np
@@ -38,7 +38,7 @@ cases = [("poisson3d 20", g.poisson3d(20), "csr", 1e-10), ("poisson3d 20", g.poi
 for name, mat, fmt, tol in cases:
     n = mat["n"]
     b = np.random.default_rng(1).standard_normal(n)
-    solvers = ["pcg", "bicgstab", "gmres"] if "convdiff" not in name else ["bicgstab", "gmres"]
+    solvers = ["pcg", "minres", "qmrs", "bicgstab", "cgs", "gmres"] if "convdiff" not in name else ["bicgstab", "gmres", "cgs"]
     for solver in solvers:
         for withK in (True, False):
             res = []
@@ -51,7 +51,7 @@ for name, mat, fmt, tol in cases:
                 P.set_option("gpus", 1)
                 res.append((r, x))
             (rm, xm), (r1, x1) = res
-            tol_it = 0.1 if (solver == "bicgstab" and "poisson" in name) else 0.02   # BiCGSTAB on Poisson: rounding-chaotic
+            tol_it = 0.1 if (solver in ("bicgstab", "cgs") and "poisson" in name) else 0.02   # BiCGSTAB / CGS on Poisson: rounding-chaotic
             good = rm[0] == r1[0] and abs(rm[1] - r1[1]) <= max(1, tol_it * r1[1]) and np.max(np.abs(xm - x1)) <= 1e-6 * max(1.0, np.max(np.abs(x1)))
             ok = ok and good
             print(f"{name:16s} {fmt} {solver:8s} K={withK}: {N} GPUs {rm} | 1 GPU {r1} | max|dx| {np.max(np.abs(xm - x1)):.2e} {'OK' if good else 'FAIL'}", flush=True)

@@ -137,6 +137,13 @@ SOLVER_CASES = [
     _c("diag1000_qmrs", ("diag", 1000), "sss", "qmrs", 1e-10, 2000, "jacobi", stable=True),
     _c("rsym5000_pcg_ssor", ("random_sym", 5000, 8, 7), "sss", "pcg", 1e-10, 500, "ssor", omega=1.2, stable=True),
     _c("rsym5000_bicgstab", ("random_sym", 5000, 8, 7), "csr", "bicgstab", 1e-10, 500, "jacobi", stable=True),
+    # CGS cases that CONVERGE and whose iteration count does not move when the reference's own C
+    # is recompiled with FMA contraction (stock / FMA build: 60 / 60, 31 / 31, 33 / 33, 9 / 9) --
+    # held to the +-2 % contract
+    _c("p2d40_csr_cgs_jacobi", ("poisson2d", 40), "csr", "cgs", 1e-8, 2000, "jacobi", stable=True),
+    _c("p3d16_csr_cgs", ("poisson3d", 16), "csr", "cgs", 1e-8, 2000, stable=True),
+    _c("cd12_csr_cgs_jacobi", ("convdiff3d", 12), "csr", "cgs", 1e-8, 2000, "jacobi", stable=True),
+    _c("rsym5000_cgs_jacobi", ("random_sym", 5000, 8, 7), "csr", "cgs", 1e-10, 500, "jacobi", stable=True),
 ]
 
 KERNEL_CASES = [
