@@ -183,6 +183,34 @@ int psp_solve_dev(int solver, const psp_operator *A, const psp_operator *K, int 
                   const double *db, double *dx, double tol, int maxit, int gmres_dim,
                   int *info, int *iter, double *relres);
 
+/* ---- Jacobi-Davidson correction equation (consumer of the path) --------- */
+
+/* The operator JDSYM hands its inner Krylov solver as both A and K:
+ * replaces CorrEq_New / CorrEq_matvec / CorrEq_precon (pysparse/eigen/src/correq.c:28-262;
+ * called from jdsym.c:570) with the search-space blocks Q, M Q and Y = K^-1 (M) Q
+ * resident on the device, so that an inner solve never crosses PCIe.
+ * optype: 1 = JDSYM_OP_UNSYM, 2 = JDSYM_OP_SYM; m and k may be NULL; kmax <= 64.
+ * The matrices and the preconditioner are borrowed and must outlive the operator. */
+typedef struct psp_correq psp_correq;
+int psp_correq_create(int optype, psp_mat *a, psp_mat *m, psp_prec *k, int kmax, psp_correq **out);
+void psp_correq_destroy(psp_correq *e);
+
+/* Upload columns [col0, col0 + ncols) of Q (which = 0), M Q (1) or Y (2) from a
+ * column-major HOST array with leading dimension ld >= n. */
+int psp_correq_set_columns(psp_correq *e, int which, int col0, int ncols, const double *host, long ld);
+
+/* Select the number of columns in use and the shift (CorrEq_update, correq.c:94-110).
+ * hinv: inverse of the leading k x k block of H = Qb' Y, row-major with leading
+ * dimension k (the reference keeps an LU factorisation instead); required when the
+ * operator has a preconditioner and k > 0, ignored otherwise. */
+int psp_correq_update(psp_correq *e, int k, double theta, const double *hinv);
+
+/* The handles to put into a psp_operator (mat for A, prec for K), or to call
+ * psp_matvec / psp_prec_apply with.  They belong to the operator: destroying
+ * them is a no-op. */
+psp_mat *psp_correq_mat(psp_correq *e);
+psp_prec *psp_correq_prec(psp_correq *e);
+
 /* Time of the device part of the most recent psp_solve / psp_solve_dev /
  * psp_matvec call, measured with CUDA events on the library stream (ms). */
 double psp_last_device_ms(void);

@@ -28,6 +28,8 @@ SYMBOLS = [
     "psp_vec_alloc", "psp_vec_free", "psp_vec_upload", "psp_vec_download", "psp_vec_fill",
     "psp_jacobi_create", "psp_ssor_create", "psp_prec_destroy", "psp_prec_apply",
     "psp_prec_apply_dev", "psp_ssor_levels", "psp_prec_set_matrix",
+    "psp_correq_create", "psp_correq_destroy", "psp_correq_set_columns", "psp_correq_update",
+    "psp_correq_mat", "psp_correq_prec",
     "psp_solve", "psp_solve_dev", "psp_last_device_ms", "psp_set_option", "psp_get_option",
     "psp_event_record", "psp_event_elapsed_ms", "psp_spmv_timing",
     "psp_dist_plan", "psp_dist_init", "psp_dist_connect", "psp_dist_shutdown", "psp_dist_info",

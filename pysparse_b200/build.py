@@ -26,7 +26,7 @@ HOST = os.path.join(PKG, "host")
 OBJ = os.path.join(ROOT, "build", "obj")
 LIB = os.path.join(PKG, "libpsp_b200.so")
 
-CU_SOURCES = ["psp_runtime.cu", "psp_spmv.cu", "psp_runs.cu", "psp_solvers.cu", "psp_precon.cu", "psp_dist.cu", "psp_multi.cu", "psp_persist.cu", "psp_persist_bicg.cu",
+CU_SOURCES = ["psp_runtime.cu", "psp_spmv.cu", "psp_runs.cu", "psp_solvers.cu", "psp_precon.cu", "psp_correq.cu", "psp_dist.cu", "psp_multi.cu", "psp_persist.cu", "psp_persist_bicg.cu",
               "psp_persist_gmres.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-I" + os.path.join(ROOT, "include")]
@@ -37,6 +37,7 @@ EXT_MODULES = {
     "sparse/spmatrix": ["spmatrixmodule.c"],
     "itsolvers/krylov": ["krylovmodule.c"],
     "precon/precon": ["preconmodule.c"],
+    "eigen/correq": ["correqmodule.c"],
 }
 
 

@@ -3,8 +3,11 @@
 #include "psp_common.cuh"
 #include "psp_multi.cuh"
 
+struct psp_correq;          // psp_correq.cuh
+
 struct psp_mat {
-  int kind = 0;             // 1 CSR, 2 SSS
+  int kind = 0;             // 1 CSR, 2 SSS, 3 operator facade (ceq != nullptr: no arrays at all)
+  psp_correq *ceq = nullptr;
   int m = 0, n = 0;
   long long nnz = 0;        // stored entries as the reference counts them (SSS: strict lower)
   // CSR arrays on the device.  For SSS this is the symmetric expansion in
@@ -43,7 +46,8 @@ struct psp_mat {
 };
 
 struct psp_prec {
-  int kind = 0;             // 1 Jacobi, 2 SSOR
+  int kind = 0;             // 1 Jacobi, 2 SSOR, 3 operator facade (ceq)
+  psp_correq *ceq = nullptr;
   int n = 0;
   double omega = 1.0;
   int steps = 1;

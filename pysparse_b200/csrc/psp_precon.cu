@@ -24,6 +24,7 @@
 #include <cooperative_groups.h>
 #include "psp_mat.cuh"
 #include "psp_vec.cuh"
+#include "psp_correq.cuh"
 #include "psp_sweep_p2p.cuh"
 
 namespace cg = cooperative_groups;
@@ -491,6 +492,7 @@ int prec_apply_dev(psp_prec *K, const double *dx, double *dy, State *gateS) {
   Ctx &c = ctx();
   const long n = K->n;
   if (n == 0) return PSP_OK;
+  if (K->ceq) return correq_apply(K->ceq, 1, dx, dy, gateS, 0);
   if (K->kind == 1) {
     const int gate = gateS ? 0 : 3;
     PSP_TRY(launch_map(FJacobiScale{dx, K->d_dinv, dy}, n, EPI_NONE, gate));
@@ -773,7 +775,7 @@ extern "C" int psp_prec_set_matrix(psp_prec *K, psp_mat *A) {
 }
 
 extern "C" void psp_prec_destroy(psp_prec *K) {
-  if (!K) return;
+  if (!K || K->ceq) return;                        // a facade belongs to its psp_correq
   multi_prec_release(K);
   cudaFree(K->d_dinv); cudaFree(K->d_t1); cudaFree(K->d_t2);
   cudaFree(K->d_rows_f); cudaFree(K->d_lptr_f); cudaFree(K->d_rows_b); cudaFree(K->d_lptr_b);

@@ -11,11 +11,11 @@
 // vectors through pinned host memory around each callback.
 #include "psp_mat.cuh"
 #include "psp_vec.cuh"
+#include "psp_correq.cuh"
 #include "psp_dist.cuh"
 
 namespace psp {
 
-int prec_apply_dev(psp_prec *K, const double *dx, double *dy, State *gateS);   // psp_precon.cu
 int pcg_persist_launch(const psp_mat *M, int n, const double *b, double *x, double *r, double *p, double *p2, double *q,
                        const double *dinv, DistMat *dm);
 int gmres_persist_launch(const psp_mat *M, int n, const double *b, double *x, double *V, double *W, double *xs,
@@ -67,15 +67,18 @@ struct Op {
   psp_prec *prec = nullptr;
   psp_callback cb = nullptr;
   void *cbctx = nullptr;
+  psp_correq *ceq = nullptr;   // device-resident correction-equation operator (psp_correq.cu), handed in as a mat / prec facade
   bool present = false;
-  bool native() const { return mat || prec; }
+  bool native() const { return mat || prec || ceq; }
 };
 
 static Op make_op(const psp_operator *o) {
   Op r;
   if (!o) return r;
   r.mat = o->mat; r.prec = o->prec; r.cb = o->cb; r.cbctx = o->ctx;
-  r.present = (r.mat || r.prec || r.cb);
+  if (r.mat && r.mat->ceq) { r.ceq = r.mat->ceq; r.mat = nullptr; }
+  if (r.prec && r.prec->ceq) { r.ceq = r.prec->ceq; r.prec = nullptr; }
+  r.present = (r.mat || r.prec || r.cb || r.ceq);
   return r;
 }
 
@@ -92,6 +95,11 @@ struct Solve {
   DistMat *dm = nullptr;
   long vstride = 0;          // distance between work vectors (0: n)
 };
+
+// no operator of this solve leaves the device: the iteration can be enqueued ahead of the GPU
+static bool device_resident(const Solve &s) {
+  return (s.A.mat || s.dm || s.A.ceq) && (s.fusedK || s.K.prec || s.K.ceq);
+}
 
 static int read_done(Solve &s, int *done) {
   Ctx &c = ctx();
@@ -141,7 +149,8 @@ static int apply_A(Solve &s, const double *dx, double *dy, const double *w1 = nu
     d.gate = gate;
     return spmv_launch(s.A.mat, dx, dy, d);
   }
-  PSP_TRY(apply_callback(s, s.A, dx, dy));
+  if (s.A.ceq) PSP_TRY(correq_apply(s.A.ceq, 0, dx, dy, s.S, gate));
+  else PSP_TRY(apply_callback(s, s.A, dx, dy));
   if (w1 || w2 || w2_is_y || epilogue != EPI_NONE) {
     FDots2 f{w1, w2_is_y ? dy : w2, dy};
     PSP_TRY(launch_map(f, s.n, epilogue, gate));
@@ -152,6 +161,7 @@ static int apply_A(Solve &s, const double *dx, double *dy, const double *w1 = nu
 // y := K^-1 x for a preconditioner that is present and not fused
 static int apply_K(Solve &s, const double *dx, double *dy) {
   if (s.K.prec) return prec_apply_dev(s.K.prec, dx, dy, s.S);
+  if (s.K.ceq) return correq_apply(s.K.ceq, 1, dx, dy, s.S, 0);
   return apply_callback(s, s.K, dx, dy);
 }
 
@@ -260,7 +270,7 @@ static int solve_pcg(Solve &s, const double *b, double *x, double *work) {
     PSP_TRY(apply_A(s, x, r));
   }
   PSP_TRY(launch_map(FPcgResid{b, r, x, s.dinv, 0}, n, s.fusedK ? EPI_PCG_RESID0_J : EPI_PCG_RESID0));
-  const bool sync_each = !((s.A.mat || s.dm) && (s.fusedK || s.K.prec));
+  const bool sync_each = !device_resident(s);
   auto body = [&](long long) -> int {
     if (s.fusedK) {
       PSP_TRY(launch_map(FPcgP{r, s.dinv, p, 0.0, 0}, n, EPI_NONE, pub));
@@ -356,7 +366,7 @@ static int solve_minres(Solve &s, const double *b, double *x, double *work) {
     PSP_TRY(apply_K(s, vh, y));
     PSP_TRY(launch_map(FDot{vh, y}, n, EPI_MINRES_BETA0));
   }
-  const bool sync_each = !((s.A.mat || s.dm) && (s.fusedK || s.K.prec));
+  const bool sync_each = !device_resident(s);
   auto body = [&](long long) -> int {
     PSP_TRY(launch_map(FMinresV{y, v, 0.0}, n, EPI_NONE, pub));
     PSP_TRY(apply_A(s, v, av, v, nullptr, false, EPI_MINRES_ALPHA));
@@ -429,7 +439,7 @@ static int solve_qmrs(Solve &s, const double *b, double *x, double *work) {
   const int pub = s.dm ? kPublish : 0;     // multi-GPU: g is read by the neighbours
   PSP_TRY(launch_map(FQmrsInit0{b, v}, n, EPI_QMRS_RHO0));
   PSP_TRY(launch_map(FQmrsInit1{v, p, g, d, x, 0.0}, n, EPI_QMRS_LOOP));
-  const bool sync_each = !((s.A.mat || s.dm) && (s.fusedK || s.K.prec));
+  const bool sync_each = !device_resident(s);
   auto body = [&](long long) -> int {
     if (s.fusedK) {
       PSP_TRY(launch_map(FDotK{v, s.dinv, nullptr}, n, EPI_QMRS_DELTA));
@@ -459,6 +469,7 @@ static int solve_qmrs(Solve &s, const double *b, double *x, double *work) {
       }
     } else {
       if (s.K.prec) PSP_TRY(prec_apply_dev(s.K.prec, x, t0, nullptr));
+      else if (s.K.ceq) PSP_TRY(correq_apply(s.K.ceq, 1, x, t0, nullptr, 3));
       else PSP_TRY(apply_callback(s, s.K, x, t0, /*check_done=*/false));
       PSP_CUDA(cudaMemcpyAsync(x, t0, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, c.stream));
     }
@@ -536,7 +547,7 @@ static int solve_bicgstab(Solve &s, const double *b, double *x, double *work) {
     PSP_TRY(apply_A(s, x, r));
   }
   PSP_TRY(launch_map(FBicgInit{b, r, rhat, x, 0}, n, EPI_BICG_RES0));
-  const bool sync_each = !((s.A.mat || s.dm) && (s.fusedK || s.K.prec));
+  const bool sync_each = !device_resident(s);
   auto body = [&](long long) -> int {
     PSP_TRY(launch_map(FBicgP{r, v, s.fusedK ? s.dinv : nullptr, p, phat, 0, 0, 0}, n, EPI_NONE, pub));
     if (!s.fusedK) PSP_TRY(apply_K(s, p, phat));
@@ -615,7 +626,7 @@ static int solve_cgs(Solve &s, const double *b, double *x, double *work) {
   } else
   PSP_TRY(apply_A(s, x, ta));
   PSP_TRY(launch_map(FCgsInit{b, ta, r0, r, u, p}, n, EPI_CGS_INIT, ident ? pub : 0));   // identity K: p itself is multiplied next
-  const bool sync_each = !((s.A.mat || s.dm) && (s.fusedK || s.K.prec));
+  const bool sync_each = !device_resident(s);
   auto body = [&](long long) -> int {
     const double *kp = p;                       // K^-1 p
     if (s.fusedK) {
@@ -721,6 +732,7 @@ static int solve_gmres(Solve &s, const double *b, double *x, int m) {
           if (s.dinv) PSP_TRY(launch_map(FScaleBy{vi, s.dinv, wi}, n, EPI_NONE, 1 | pub));
         } else {
           if (s.K.prec) PSP_TRY(prec_apply_dev(s.K.prec, vi, wi, s.S));
+          else if (s.K.ceq) PSP_TRY(correq_apply(s.K.ceq, 1, vi, wi, s.S, 1));
           else {
             // callback: must not run once the cycle is over
             PSP_CUDA(cudaMemcpyAsync(c.h_state, c.state, sizeof(State), cudaMemcpyDeviceToHost, c.stream));
@@ -729,7 +741,7 @@ static int solve_gmres(Solve &s, const double *b, double *x, int m) {
             PSP_TRY(apply_callback(s, s.K, vi, wi, false));
           }
         }
-        if (!s.A.mat && !s.dm) {
+        if (!s.A.mat && !s.dm && !s.A.ceq) {
           PSP_CUDA(cudaMemcpyAsync(c.h_state, c.state, sizeof(State), cudaMemcpyDeviceToHost, c.stream));
           PSP_CUDA(cudaStreamSynchronize(c.stream));
           if (c.h_state->done || c.h_state->cyc_done) break;

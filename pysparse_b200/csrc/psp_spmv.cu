@@ -33,6 +33,7 @@
 // y[i]; the lower triangle + diagonal are kept as well for the SSOR sweeps.
 #include <climits>
 #include "psp_mat.cuh"
+#include "psp_correq.cuh"
 #include "psp_epilogue.cuh"
 #include "psp_tma_ring.cuh"
 
@@ -457,6 +458,11 @@ static int spmv_dispatch(const psp_mat *A, const double *dx, double *dy, const S
 int spmv_launch(const psp_mat *A, const double *dx, double *dy, const SpmvDots &d) {
   Ctx &c = ctx();
   if (A->m == 0) return PSP_OK;
+  if (A->ceq) {
+    // operator facade (psp_correq.cu); the solvers unwrap it themselves and add their reductions
+    if (d.w1 || d.w2 || d.w2_is_y || d.epilogue != EPI_NONE) { set_error("spmv: fused reductions on an operator handle"); return PSP_ERR_ARG; }
+    return correq_apply(A->ceq, 0, dx, dy, d.S, d.gate);
+  }
   bool sample = false;
   if (c.spmv_sample > 0) {
     sample = (c.spmv_seen % c.spmv_sample == 0) && c.spmv_pairs < Ctx::kSpmvPairs;
@@ -557,7 +563,7 @@ extern "C" int psp_sss_create(int n, int nnz, const int *ind, const int *col, co
 }
 
 extern "C" void psp_mat_destroy(psp_mat *A) {
-  if (!A) return;
+  if (!A || A->ceq) return;                        // a facade belongs to its psp_correq
   if (A->multi) { multi_detach(A->multi); A->multi = nullptr; }
   if (A->transp) psp_mat_destroy(A->transp);
   cudaFree(A->d_ind); cudaFree(A->d_col); cudaFree(A->d_val); cudaFree(A->d_blk); cudaFree(A->d_blk_halo);

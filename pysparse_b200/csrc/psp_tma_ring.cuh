@@ -192,19 +192,74 @@ struct Ring {
             rowop(r0 + tid, sum);
           }
         } else {
-          // longer rows: a group of 8 / 16 / 32 lanes per row, chosen from the block's mean
-          // row length so that a CTA keeps 32 / 16 / 8 rows (and their x gathers) in flight
-          // longer rows: one warp per row.  (Measured alternatives on the 2^22-row power-law
-          // matrix, 1118 us: 8-lane groups per row 1331 us; entry-parallel products in place +
-          // segmented sums 1208 us -- the kernel is bound by the 32-byte L2 sectors fetched
-          // per 8-byte random x gather, not by how the rows are mapped to lanes.)
-          const int w = tid >> 5, l = tid & 31;
-          for (int rr = w; rr < nrows; rr += kThreads / 32) {
-            const int s = sind[roff + rr] - base, e = sind[roff + rr + 1] - base;
-            double sum = 0.0;
-            for (int k = s + l; k < e; k += 32) sum += sval[k] * (NC ? ldg_f64(x + scol[k]) : x[scol[k]]);
-            sum = warp_sum(sum);
-            if (l == 0) rowop(r0 + rr, sum);
+          // longer / irregular rows (mean > 16 entries): two phases per block.
+          // (1) entry-parallel: thread t takes entries t, t + 256, ... -- its x gathers are
+          //     independent and go out four at a time (a row-per-warp walk has ONE gather in flight
+          //     per warp and spends its time waiting for L2: 113 G gathers/s on the 2^22-row
+          //     power-law matrix, where the chip sustains 200); the rounded products replace the
+          //     values in the stage buffer.
+          // (2) one thread per row adds its products in row order -- the reference's order, so
+          //     these rows are bit-identical to it as well; rows longer than kSeqRow are left to
+          //     whole warps (strided partial sums, then a shuffle tree).
+          constexpr int kSeqRow = 96;
+          __shared__ int long_rows[kBlkNnz / kSeqRow + 2];
+          __shared__ int n_long;
+          double *pv = const_cast<double *>(sval);
+          const int kb = k0 - base, ke = k1 - base;
+          if (tid == 0) n_long = 0;
+#ifndef PSP_IRR_BATCH
+#define PSP_IRR_BATCH 4                              // eight at once spill under the 32-register cap
+#endif
+#ifdef PSP_IRR_PLAIN
+#define PSP_IRR_LOAD(p) (*(p))
+#else
+#define PSP_IRR_LOAD(p) (NC ? ldg_f64(p) : *(p))
+#endif
+#pragma unroll 1
+          for (int h = 0; h < 8; h += PSP_IRR_BATCH) {
+            double xv[PSP_IRR_BATCH];
+#pragma unroll
+            for (int j = 0; j < PSP_IRR_BATCH; j++) {
+              const int k = kb + tid + (h + j) * kThreads;
+              xv[j] = (k < ke) ? PSP_IRR_LOAD(x + scol[k]) : 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < PSP_IRR_BATCH; j++) {
+              const int k = kb + tid + (h + j) * kThreads;
+              if (k < ke) pv[k] = __dmul_rn(sval[k], xv[j]);
+            }
+          }
+          wrote_stage = true;
+          __syncthreads();
+          if (tid < nrows) {
+            const int s = sind[roff + tid] - base, e = sind[roff + tid + 1] - base;
+            if (e - s <= kSeqRow) {
+              double sum = 0.0;
+              for (int k = s; k < e; k += 8) {
+                double pr[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) pr[j] = (k + j < e) ? pv[k + j] : 0.0;
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                  if (k + j < e) sum = __dadd_rn(sum, pr[j]);
+              }
+              rowop(r0 + tid, sum);
+            } else {
+              long_rows[atomicAdd(&n_long, 1)] = tid;
+            }
+          }
+          __syncthreads();
+          const int nl = n_long;
+          if (nl > 0) {
+            const int w = tid >> 5, l = tid & 31;
+            for (int q = w; q < nl; q += kThreads / 32) {
+              const int rr = long_rows[q];
+              const int s = sind[roff + rr] - base, e = sind[roff + rr + 1] - base;
+              double sum = 0.0;
+              for (int k = s + l; k < e; k += 32) sum += pv[k];
+              sum = warp_sum(sum);
+              if (l == 0) rowop(r0 + rr, sum);
+            }
           }
         }
       } else {

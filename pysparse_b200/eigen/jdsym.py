@@ -12,15 +12,30 @@ correction equation reaches the solver as a duck-typed operator object with ``sh
 ``matvec`` and ``precon``, exactly what ``ItSolvers_Solve`` (``spmatrixmodule.c:266-307``)
 hands to it in the reference; the outer iteration (Rayleigh-Ritz on a search space of at most
 ``jmax`` vectors, Gram-Schmidt, restarts, bookkeeping) is small dense algebra on the host
-(LAPACK/BLAS there, NumPy here).  A native correction-equation operator that keeps the search
-space on the device is the next step.
+(LAPACK/BLAS there, NumPy here).
+
+When ``A``, ``M`` and ``K`` are objects of this package the correction equation itself is a
+device object as well (``pysparse_b200.eigen.correq``, ``csrc/psp_correq.cu``): the blocks
+``Q``, ``M Q`` and ``Y`` are mirrored in HBM -- only the columns that changed are uploaded
+before a correction equation -- and the operator exposes the ``_psp_mat`` / ``_psp_prec`` handles
+by which ``krylov.*`` recognises a native operand, so an inner solve runs without a single
+vector crossing PCIe.  With foreign operators (anything that only has ``matvec`` / ``precon``)
+the operator below does the same arithmetic in NumPy around their callbacks.
 """
 import numpy as np
+
+from . import correq as _device_correq
+
+_DEVICE_KMAX = 64            # kCeqMaxK of csrc/psp_correq.cuh
 
 __all__ = ["jdsym", "CorrEq", "JDSYM_OP_UNSYM", "JDSYM_OP_SYM"]
 
 JDSYM_OP_UNSYM = 1
 JDSYM_OP_SYM = 2
+
+#: False: keep the correction equation on the host-callback protocol even for device operands
+#: (parity tests compare the two)
+DEVICE_CORREQ = True
 
 
 # ---------------------------------------------------------------- operator helpers
@@ -85,16 +100,49 @@ class CorrEq:
     selects the number of locked vectors and the shift, ``right(r)`` projects a residual
     into the right-hand side in place."""
 
-    def __init__(self, optype, n, amat, mmat, prec, Q, Qm, Y, H):
+    def __init__(self, optype, n, amat, mmat, prec, Q, Qm, Y, H, device=True):
         self.optype, self.n = optype, n
         self.amat, self.mmat, self.prec = amat, mmat, prec
         self.Q, self.Qm, self.Y, self.H = Q, Qm, Y, H
         self.shape = (n, n)
         self.k = 0
         self.theta = 0.0
+        self._dev = None
+        self._synced = 0                             # columns below this index are up to date on the device
+        if device and n > 0 and Q.shape[1] <= _DEVICE_KMAX:
+            try:
+                self._dev = _device_correq.operator(optype, amat, mmat, prec, Q.shape[1])
+            except TypeError:                        # a foreign operand: stay on the callback protocol
+                self._dev = None
 
-    def update(self, k, theta):
+    @property
+    def _psp_mat(self):
+        if self._dev is None:
+            raise AttributeError("_psp_mat")
+        return self._dev._psp_mat
+
+    @property
+    def _psp_prec(self):
+        if self._dev is None:
+            raise AttributeError("_psp_prec")
+        return self._dev._psp_prec
+
+    def update(self, k, theta, stable=0):
+        """Use the first ``k`` columns and the shift ``theta``.  ``stable``: columns below this
+        index have not been written since the previous call (the locked eigenvectors)."""
         self.k, self.theta = k, theta
+        if self._dev is None:
+            return
+        lo = min(self._synced, stable, k)
+        if lo < k:
+            self._dev.set_columns(0, lo, self.Q[:, lo:k])
+            if self.mmat is not None:
+                self._dev.set_columns(1, lo, self.Qm[:, lo:k])
+            if self.prec is not None:
+                self._dev.set_columns(2, lo, self.Y[:, lo:k])
+        self._synced = min(stable, k)
+        hinv = np.linalg.inv(self.H[:k, :k]) if (self.prec is not None and k > 0) else None
+        self._dev.update(k, float(theta), hinv)
 
     # y := (A - theta M) x   /   (A - theta I) x
     def _a_theta(self, x):
@@ -132,6 +180,8 @@ class CorrEq:
             _mgs(r, self.k, self.Q)
 
     def matvec(self, x, y):
+        if self._dev is not None:
+            return self._dev.matvec(x, y)
         x = np.ascontiguousarray(x, dtype=np.float64)
         t = self._a_theta(x)
         if self.optype == JDSYM_OP_SYM:
@@ -145,6 +195,8 @@ class CorrEq:
             y[:] = self._project1(self.Q, self.Q, t)
 
     def precon(self, x, y):
+        if self._dev is not None:
+            return self._dev.precon(x, y)
         x = np.ascontiguousarray(x, dtype=np.float64)
         if self.optype == JDSYM_OP_SYM:
             if self.prec is not None:
@@ -243,7 +295,7 @@ def jdsym(A, M, K, kmax, tau, jdtol, itmax, linsolver, jmax=25, jmin=10, blksize
     resnrm = np.zeros(blksize)
     lam = np.zeros(kmax)
     Mp = np.zeros((jmax + blksize, jmax + blksize))     # interaction matrix V'AV, upper triangle
-    correq = CorrEq(optype, n, A, M, K, Q, Qm, Y, H)
+    correq = CorrEq(optype, n, A, M, K, Q, Qm, Y, H, device=DEVICE_CORREQ)
     project = (lambda v: projector.project(v)) if projector is not None else None
 
     # ---- initial search space (jdsym.c:212-262)
@@ -357,7 +409,7 @@ def jdsym(A, M, K, kmax, tau, jdtol, itmax, linsolver, jmax=25, jmin=10, blksize
         for act in range(actblksize):
             v = np.zeros(n)
             r = np.ascontiguousarray(Res[:, act])
-            correq.update(k + actblksize, float(s[act]) if resnrm[act] < eps_tr else tau)
+            correq.update(k + actblksize, float(s[act]) if resnrm[act] < eps_tr else tau, stable=k)
             it_tol = toldecay ** (-solvestep[act])
             solvestep[act] += 1
             correq.right(r)

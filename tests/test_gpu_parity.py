@@ -53,6 +53,15 @@ def test_spmv_and_precon_kernels_vs_golden(gpu, native, kc, variant):
         # row blocks averaging <= 16 entries per row keep the reference's summation order
         if key not in ("pow_3000", "tendigit_500"):
             assert np.array_equal(y, G[key + "/csr_y"]) and np.array_equal(yt, G[key + "/csr_yt"])
+        elif variant in (3, 4, "auto"):
+            # irregular blocks (TMA-ring kernels): products entry-parallel, then every row of at most
+            # 96 entries is added by one thread in row order -- bit-identical; only longer rows are
+            # summed by a warp (psp_tma_ring.cuh)
+            val, col, ind = mat["csr"]
+            short = np.diff(ind) <= 96
+            assert short.any() and np.array_equal(y[short], G[key + "/csr_y"][short])
+            short_t = np.bincount(col, minlength=shape[1]) <= 96
+            assert np.array_equal(yt[short_t], G[key + "/csr_yt"][short_t])
         if "sss" in mat:
             S = gpu.sss(n, *mat["sss"])
             ys = np.full(n, np.nan); gpu.matvec(S, x, ys)

@@ -185,3 +185,28 @@ def test_verbose_output_format(jd, capsys):
     assert "JDSYM     Solving  A*x = lambda*x  without preconditioning." in out
     assert "  IT   K   J       RES CGIT RITZVALS(1:5)" in out
     assert "JDSYM execution statistics" in out and "LAMBDA(I)" in out
+
+
+def test_device_operator_module_rejects_foreign_operands_without_touching_the_gpu():
+    """eigen/correq (the device-resident correction equation) only accepts device objects; jdsym's
+    own operator then stays on the callback protocol (no GPU is needed to find that out)."""
+    from pysparse_b200.eigen import correq, jdsym as J
+
+    class Foreign:
+        shape = (5, 5)
+
+        def matvec(self, x, y):
+            y[:] = 2.0 * x
+
+    with pytest.raises(TypeError):
+        correq.operator(2, Foreign(), None, None, 3)
+    with pytest.raises(TypeError):
+        correq.operator(2, object(), None, None, 3)
+    ce = J.CorrEq(2, 5, Foreign(), None, None, np.zeros((5, 3), order="F"), None, None, None)
+    assert ce._dev is None
+    with pytest.raises(AttributeError):
+        ce._psp_mat
+    ce.update(0, 0.5)
+    y = np.empty(5)
+    ce.matvec(np.ones(5), y)
+    assert np.allclose(y, 1.5)
