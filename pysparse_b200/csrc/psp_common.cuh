@@ -130,7 +130,7 @@ struct Ctx {
   long long spmv_format = -1; // device layout chosen at matrix creation: -1 automatic, 0 CSR row blocks, 1 diagonal runs
   // per-device launch caches (occupancy, "attribute already set"): a context is one device, and
   // cudaFuncSetAttribute is per device -- nothing of this kind may live in a function-static
-  int occ_tma[2][2] = {{0, 0}, {0, 0}}, occ_tma_cap[2][2] = {{-1, -1}, {-1, -1}};   // k_spmv_tma<STAGES-2, DOTS>
+  int occ_tma[3][2] = {{0, 0}, {0, 0}, {0, 0}}, occ_tma_cap[3][2] = {{-1, -1}, {-1, -1}, {-1, -1}};   // k_spmv_tma<STAGES-2, DOTS>
   int occ_stream[2][2] = {{0, 0}, {0, 0}};                                          // k_spmv_stream<VEC, DOTS>
   int occ_sweep_grid[2] = {0, 0};
   size_t sweep_cta_smem[2] = {0, 0};

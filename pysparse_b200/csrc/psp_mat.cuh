@@ -19,6 +19,7 @@ struct psp_mat {
   double *d_val = nullptr;
   // row-block schedule of the streaming SpMV kernel
   int nb = 0;
+  bool irregular = false;   // mean row longer than 16 entries: the blocks take the entry-parallel path (psp_tma_ring.cuh)
   int nint = 0;             // leading blocks that read no halo column (== nb unless sharded)
   int *d_blk = nullptr;
   int *d_blk_halo = nullptr; // sharded slabs: per block, [first, end) of the halo positions it reads (int2)

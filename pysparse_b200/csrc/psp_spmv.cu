@@ -216,10 +216,14 @@ __global__ void __launch_bounds__(kThreads) k_spmv_tma(SpmvArgs a) {
   }
 }
 
+#ifndef PSP_IRR_VARIANT
+#define PSP_IRR_VARIANT 4
+#endif
+
 template <int STAGES, bool DOTS>
 static int launch_tma(const SpmvArgs &a, int nb, int ctas_per_sm) {
   Ctx &c = ctx();
-  static_assert(STAGES == 2 || STAGES == 3, "launch cache is indexed by STAGES - 2");
+  static_assert(STAGES >= 2 && STAGES <= 4, "launch cache is indexed by STAGES - 2");
   int &resident = c.occ_tma[STAGES - 2][DOTS ? 1 : 0], &cached_cap = c.occ_tma_cap[STAGES - 2][DOTS ? 1 : 0];
   const int smem_bytes = STAGES * kStageBytes;
   if (resident == 0 || cached_cap != ctas_per_sm) {
@@ -294,6 +298,7 @@ static int finish_csr_upload(psp_mat *A, const std::vector<int> &ind, const int 
   build_row_blocks(A->m, ind.data(), rows);
   A->nb = (int)rows.size() - 1;
   A->nint = A->nb;
+  A->irregular = A->m > 0 && ind[A->m] > 16LL * A->m;
   order.reserve((size_t)A->nb);
   if (own_cols >= 0) {
     std::vector<int> boundary;
@@ -490,11 +495,20 @@ static int spmv_dispatch(const psp_mat *A, const double *dx, double *dy, const S
   a.l2_stream = l2_stream_for(A->m);
   a.partials = c.partials; a.ticket = c.tickets; a.aux = nullptr;
   if (d.S) a.aux = (void *)(d.S + 1);   // solver-specific small state sits right behind the State
-  if (c.spmv_variant == 3 || c.spmv_variant == 0) {
+  // ring depth: 2 stages (4 CTAs per SM) for stencil-like rows; matrices whose blocks take the
+  // entry-parallel path (mean row > 16 entries) spend a block's time between barriers, not in the
+  // stream, and want the next blocks to be there already: deeper ring, fewer CTAs
+  // (power-law 2^21 rows: 538 us with 2 stages, 460 with 3; profiles/r2_irregular_notes.md)
+  int variant = c.spmv_variant;
+  if (variant == 0) variant = A->irregular ? PSP_IRR_VARIANT : 3;
+  if (variant == 3) {
     return d.S ? launch_tma<2, true>(a, A->nb, (int)c.spmv_ctas) : launch_tma<2, false>(a, A->nb, (int)c.spmv_ctas);
   }
-  if (c.spmv_variant == 4) {
+  if (variant == 4) {
     return d.S ? launch_tma<3, true>(a, A->nb, (int)c.spmv_ctas) : launch_tma<3, false>(a, A->nb, (int)c.spmv_ctas);
+  }
+  if (variant == 5) {
+    return d.S ? launch_tma<4, true>(a, A->nb, (int)c.spmv_ctas) : launch_tma<4, false>(a, A->nb, (int)c.spmv_ctas);
   }
   const bool vec = (c.spmv_variant != 1);
   // persistent grid: exactly the number of CTAs that are resident at once

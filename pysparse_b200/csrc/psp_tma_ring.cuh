@@ -201,7 +201,13 @@ struct Ring {
           // (2) one thread per row adds its products in row order -- the reference's order, so
           //     these rows are bit-identical to it as well; rows longer than kSeqRow are left to
           //     whole warps (strided partial sums, then a shuffle tree).
-          constexpr int kSeqRow = 96;
+          // Measured on the 2^21-row power-law matrix (profiles/r2_irregular_notes.md): the gather
+          // flavour (ld.global.nc or plain) and the batch (2 / 4 / 8) make no difference, the ring
+          // depth does (2 / 3 / 4 stages: 538 / 462 / 657 us), kSeqRow 96 / 48 / 32: 462 / 437 / 446 us.
+#ifndef PSP_IRR_SEQ
+#define PSP_IRR_SEQ 48
+#endif
+          constexpr int kSeqRow = PSP_IRR_SEQ;
           __shared__ int long_rows[kBlkNnz / kSeqRow + 2];
           __shared__ int n_long;
           double *pv = const_cast<double *>(sval);

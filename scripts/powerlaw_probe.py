@@ -8,7 +8,12 @@ from pysparse_b200.tools import gallery as g
 
 peak = 6549.0
 for lg in [int(a) for a in sys.argv[1:]] or [21, 22]:
-    mat = g.powerlaw(1 << lg)
+    cache = f"/tmp/powerlaw_{lg}.npz"                 # the generator takes longer than the measurement
+    if os.path.exists(cache):
+        z = np.load(cache); mat = {"shape": tuple(z["shape"]), "csr": (z["val"], z["col"], z["ind"])}
+    else:
+        mat = g.powerlaw(1 << lg)
+        np.savez(cache, shape=np.array(mat["shape"]), val=mat["csr"][0], col=mat["csr"][1], ind=mat["csr"][2])
     m, n = mat["shape"]
     val, col, ind = mat["csr"]
     A = P.Matrix.csr(m, n, val, col, ind)

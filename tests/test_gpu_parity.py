@@ -55,12 +55,12 @@ def test_spmv_and_precon_kernels_vs_golden(gpu, native, kc, variant):
             assert np.array_equal(y, G[key + "/csr_y"]) and np.array_equal(yt, G[key + "/csr_yt"])
         elif variant in (3, 4, "auto"):
             # irregular blocks (TMA-ring kernels): products entry-parallel, then every row of at most
-            # 96 entries is added by one thread in row order -- bit-identical; only longer rows are
+            # 48 entries is added by one thread in row order -- bit-identical; only longer rows are
             # summed by a warp (psp_tma_ring.cuh)
             val, col, ind = mat["csr"]
-            short = np.diff(ind) <= 96
+            short = np.diff(ind) <= 48
             assert short.any() and np.array_equal(y[short], G[key + "/csr_y"][short])
-            short_t = np.bincount(col, minlength=shape[1]) <= 96
+            short_t = np.bincount(col, minlength=shape[1]) <= 48
             assert np.array_equal(yt[short_t], G[key + "/csr_yt"][short_t])
         if "sss" in mat:
             S = gpu.sss(n, *mat["sss"])
