@@ -93,41 +93,68 @@ struct Seg { int key; int t0, len; int x0; int kpos; };     // key: (global) dia
 struct RunBuild {
   std::vector<int> blk;        // 4 ints per block, natural order
   std::vector<int> seg;        // 4 ints per run
-  std::vector<double> val;
+  std::vector<double> val;     // run values; kRunSkip in the bridged gaps
+  long long diag_off = 0;      // SSS: position of the diagonal in val
 };
 
-// Runs of the rows [r0, r1) of a CSR structure.  A run continues from row t-1 to row t when
-// both rows have an entry on the same (global) diagonal and the local column advances by one.
+double skip_value() { double v; const unsigned long long b = kRunSkip; memcpy(&v, &b, 8); return v; }
+
+// Runs of the rows [r0, r1) of a CSR structure.  A run continues to row t when the row has an
+// entry on the same (global) diagonal whose local column continues the run -- directly, or
+// (bridge) after at most kRunGapMax rows without one, once the run is kRunGapMinLen rows long.
 // entry_seg[k - ind[r0]] receives the block-local run number of entry k.
-void scan_block(const int *ind, const int *col, const int *gcol, int grow0, int r0, int r1, std::vector<Seg> &segs,
-                std::vector<int> *entry_seg) {
+void scan_block(const int *ind, const int *col, const int *gcol, int grow0, int r0, int r1, bool bridge,
+                std::vector<Seg> &segs, std::vector<int> *entry_seg) {
   struct Open { int key, id; };
-  static thread_local std::vector<Open> prev, cur;
-  prev.clear();
+  static thread_local std::vector<Open> open, keep;     // runs that ended at most kRunGapMax rows ago, by key
+  open.clear();
   segs.clear();
   const int k0 = ind[r0];
   if (entry_seg) entry_seg->resize((size_t)(ind[r1] - k0));
   for (int r = r0; r < r1; r++) {
     const int t = r - r0;
-    cur.clear();
+    keep.clear();
     size_t p = 0;
     for (int k = ind[r]; k < ind[r + 1]; k++) {
       const int key = (gcol ? gcol[k] : col[k]) - (grow0 + r);
-      while (p < prev.size() && prev[p].key < key) p++;
+      while (p < open.size() && open[p].key < key) {
+        const Seg &o = segs[(size_t)open[p].id];
+        if (bridge && t - (o.t0 + o.len) < kRunGapMax) keep.push_back(open[p]);     // may still be continued by a later row
+        p++;
+      }
       int id = -1;
-      if (p < prev.size() && prev[p].key == key) {
-        Seg &s = segs[(size_t)prev[p].id];
-        if (s.x0 + s.len == col[k]) { id = prev[p].id; s.len++; }
+      if (p < open.size() && open[p].key == key) {
+        Seg &s = segs[(size_t)open[p].id];
+        const int gap = t - (s.t0 + s.len);
+        if (s.x0 + s.len + gap == col[k] && (gap == 0 || (bridge && gap <= kRunGapMax && s.len >= kRunGapMinLen))) {
+          id = open[p].id;
+          s.len += gap + 1;
+        }
+        p++;
       }
       if (id < 0) {
         id = (int)segs.size();
         segs.push_back(Seg{key, t, 1, col[k], 0});
       }
       if (entry_seg) (*entry_seg)[(size_t)(k - k0)] = id;
-      cur.push_back(Open{key, id});
+      keep.push_back(Open{key, id});
     }
-    prev.swap(cur);
+    for (; p < open.size(); p++) {
+      const Seg &o = segs[(size_t)open[p].id];
+      if (bridge && t - (o.t0 + o.len) < kRunGapMax) keep.push_back(open[p]);
+    }
+    open.swap(keep);
   }
+}
+
+// no stored value may look like the gap marker
+bool can_bridge(const double *val, long long nnz, const double *diag, int n) {
+  for (long long k = 0; k < nnz; k++)
+    if (run_skip(val[k])) return false;
+  if (diag)
+    for (int i = 0; i < n; i++)
+      if (run_skip(diag[i])) return false;
+  return true;
 }
 
 // cheap look at a sample of blocks: is the format worth a full analysis?
@@ -141,7 +168,7 @@ bool sample_accepts(int m, const int *ind, const int *col, const int *gcol, int 
     const int b = (int)((long long)i * nb / nsample);
     const int r0 = b * kThreads, r1 = std::min(m, r0 + kThreads);
     if ((long long)ind[r1] - ind[r0] > 64 * kThreads) return false;    // long rows: not this format's case
-    scan_block(ind, col, gcol, grow0, r0, r1, segs, nullptr);
+    scan_block(ind, col, gcol, grow0, r0, r1, true, segs, nullptr);
     nseg += (long long)segs.size();
     nent += ind[r1] - ind[r0];
   }
@@ -224,6 +251,22 @@ bool by_key_then_row(const Seg &a, const Seg &b) { return a.key != b.key ? a.key
 
 }  // namespace
 
+// A block whose runs cover a bridged gap is flagged (bit kRunGapFlag of its row count): only there
+// does the kernel test the loaded values for the marker.
+static void flag_gap_blocks(RunBuild &rb) {
+  const size_t nb = rb.blk.size() / 4;
+  const unsigned long long *bits = reinterpret_cast<const unsigned long long *>(rb.val.data());
+  for (size_t b = 0; b < nb; b++) {
+    bool gap = false;
+    for (int sgi = rb.blk[4 * b + 2]; sgi < rb.blk[4 * b + 3] && !gap; sgi++) {
+      const size_t k0 = (size_t)rb.seg[4 * (size_t)sgi], len = (size_t)rb.seg[4 * (size_t)sgi + 3];
+      for (size_t u = 1; u + 1 < len; u++)           // a gap is strictly inside its run
+        if (bits[k0 + u] == kRunSkip) { gap = true; break; }
+    }
+    if (gap) rb.blk[4 * b + 1] |= kRunGapFlag;
+  }
+}
+
 // Automatic choice: the run kernels win once the matrix stream is far beyond what L2 and the
 // latency of one pass can hide (measured on 3-D Poisson, PCG us/iteration, runs vs row blocks:
 // 192^3 255 vs 238, 256^3 493 vs 545; SpMV 256^3 228 vs 288 us) -- below ~1 GB of CSR stream
@@ -237,14 +280,16 @@ static bool build_csr_runs(int m, const int *ind, const int *col, const double *
   if (m == 0 || nnz == 0) return false;
   if (!force && !sample_accepts(m, ind, col, gcol, grow0)) return false;
   const int nb = (m + kThreads - 1) / kThreads;
+  const bool bridge = can_bridge(val, nnz, nullptr, 0);
+  const double skip = skip_value();
   rb.blk.resize(4 * (size_t)nb);
-  rb.val.resize((size_t)nnz);
+  rb.val.reserve((size_t)nnz + (size_t)nnz / 64);
   std::vector<Seg> segs;
   std::vector<int> entry_seg, order;
   long long kpos = 0;
   for (int b = 0; b < nb; b++) {
     const int r0 = b * kThreads, r1 = std::min(m, r0 + kThreads);
-    scan_block(ind, col, gcol, grow0, r0, r1, segs, &entry_seg);
+    scan_block(ind, col, gcol, grow0, r0, r1, bridge, segs, &entry_seg);
     order.resize(segs.size());
     for (size_t i = 0; i < segs.size(); i++) order[i] = (int)i;
     std::sort(order.begin(), order.end(), [&](int x, int y) { return by_key_then_row(segs[(size_t)x], segs[(size_t)y]); });
@@ -252,11 +297,13 @@ static bool build_csr_runs(int m, const int *ind, const int *col, const double *
     rb.blk[4 * (size_t)b + 2] = (int)(rb.seg.size() / 4);
     for (int id : order) {
       Seg &s = segs[(size_t)id];
+      if (kpos + s.len >= (1LL << 31)) return false;
       s.kpos = (int)kpos;
       kpos += s.len;
       rb.seg.push_back(s.kpos); rb.seg.push_back(s.x0); rb.seg.push_back(s.t0); rb.seg.push_back(s.len);
     }
     rb.blk[4 * (size_t)b + 3] = (int)(rb.seg.size() / 4);
+    rb.val.resize((size_t)kpos, skip);               // bridged gaps keep the marker
     const int k0 = ind[r0];
     for (int r = r0; r < r1; r++)
       for (int k = ind[r]; k < ind[r + 1]; k++) {
@@ -267,6 +314,7 @@ static bool build_csr_runs(int m, const int *ind, const int *col, const double *
     if (!force && (b & 1023) == 1023 && (long long)(rb.seg.size() / 4) * 8 > (long long)ind[r1]) return false;
   }
   if (!force && (long long)(rb.seg.size() / 4) * 16 > nnz) return false;     // mean run shorter than 16 rows
+  flag_gap_blocks(rb);
   return true;
 }
 
@@ -283,48 +331,96 @@ int runs_try_csr(psp_mat *A, const int *ind, const int *col, const double *val, 
   return PSP_OK;
 }
 
-static bool build_sss_runs(int n, const int *ind, const int *col, const double *val, const double *diag, bool force,
-                           RunBuild &rb) {
+// SSS: the strict lower triangle is scanned block by block.  Two value layouts:
+//  * block-major (global_major == false): a block's lower runs are stored back to back; the
+//    mirrored (upper) runs of a target block are slices of the source blocks' runs, so a run that
+//    crosses a source-block boundary inside the target block gives two descriptors;
+//  * global-run-major: runs that continue across a block boundary are chained into GLOBAL runs and
+//    the values are stored global-run-major (sorted by diagonal, then row); lower and mirrored
+//    runs of a block are slices of the global runs -- ONE descriptor per diagonal for an interior
+//    block of a stencil matrix however the grid lines fall into the blocks.
+// over_budget: number of blocks that need more than one batch (8 descriptors) in run_pass.
+static bool build_sss_runs_layout(int n, const int *ind, const int *col, const double *val, const double *diag, bool force,
+                                  bool global_major, RunBuild &rb, long long *over_budget) {
   const long long nnz = ind[n];
-  if (n == 0) return false;
-  if (nnz > 0 && !force && !sample_accepts(n, ind, col, nullptr, 0)) return false;
-  if (nnz + n >= (1LL << 31)) return false;
   const int nb = (n + kThreads - 1) / kThreads;
-  rb.val.resize((size_t)nnz + (size_t)n);
-  std::copy(diag, diag + n, rb.val.begin() + nnz);
-  struct Upper { int tb; Seg s; };
-  std::vector<std::vector<Seg>> lower((size_t)nb);
-  std::vector<Upper> upper;
+  const bool bridge = can_bridge(val, nnz, diag, n);
+  const double skip = skip_value();
+  struct GRun { int key, row0, len; long long pos; };
+  struct LSeg { Seg s; int grun; };                  // s.kpos is filled in once the positions are known
+  std::vector<GRun> gruns;
+  std::vector<std::vector<LSeg>> lower((size_t)nb);
   std::vector<Seg> segs;
-  std::vector<int> entry_seg;
-  long long kpos = 0;
+  struct Tail { int key, grun, xend; };              // runs that reach the last row of the previous block
+  std::vector<Tail> tails, tails_next;
+  // pass 1: structure
   for (int b = 0; b < nb; b++) {
     const int r0 = b * kThreads, r1 = std::min(n, r0 + kThreads);
-    scan_block(ind, col, nullptr, 0, r0, r1, segs, &entry_seg);
-    std::vector<int> order(segs.size());
-    for (size_t i = 0; i < segs.size(); i++) order[i] = (int)i;
-    std::sort(order.begin(), order.end(), [&](int x, int y) { return by_key_then_row(segs[(size_t)x], segs[(size_t)y]); });
-    for (int id : order) {
-      Seg &s = segs[(size_t)id];
-      s.kpos = (int)kpos;
-      kpos += s.len;
-      lower[(size_t)b].push_back(s);
-      // the mirrored use of the same values: entry (i, j) adds val * x[i] to y[j]; rows
-      // i0 .. i0+len-1 of this run are the columns of target rows j0 .. j0+len-1, j0 = i0 + key
-      int i0 = r0 + s.t0, j0 = i0 + s.key, left = s.len, kp = s.kpos;
-      while (left > 0) {
-        const int tb = j0 / kThreads, tt = j0 % kThreads;
-        const int piece = std::min(left, kThreads - tt);
-        upper.push_back(Upper{tb, Seg{-s.key, tt, piece, i0, kp}});
-        i0 += piece; j0 += piece; kp += piece; left -= piece;
+    scan_block(ind, col, nullptr, 0, r0, r1, bridge, segs, nullptr);
+    tails_next.clear();
+    for (const Seg &s : segs) {
+      int g = -1;
+      if (global_major && s.t0 == 0)
+        for (const Tail &t : tails)
+          if (t.key == s.key && t.xend == s.x0) { g = t.grun; break; }
+      if (g < 0) {
+        g = (int)gruns.size();
+        gruns.push_back(GRun{s.key, r0 + s.t0, 0, 0});
       }
+      gruns[(size_t)g].len += s.len;
+      lower[(size_t)b].push_back(LSeg{s, g});
+      if (s.t0 + s.len == r1 - r0) tails_next.push_back(Tail{s.key, g, s.x0 + s.len});
+    }
+    tails.swap(tails_next);
+  }
+  // positions: global-run-major by (diagonal, row); block-major by (block, diagonal, row) --
+  // without chaining every run is its own "global" run and starts in exactly one block
+  {
+    std::vector<int> order(gruns.size());
+    for (size_t i = 0; i < order.size(); i++) order[i] = (int)i;
+    std::sort(order.begin(), order.end(), [&](int x, int y) {
+      const GRun &a = gruns[(size_t)x], &c = gruns[(size_t)y];
+      if (!global_major && a.row0 / kThreads != c.row0 / kThreads) return a.row0 < c.row0;
+      return a.key != c.key ? a.key < c.key : a.row0 < c.row0;
+    });
+    long long pos = 0;
+    for (int id : order) { gruns[(size_t)id].pos = pos; pos += gruns[(size_t)id].len; }
+    if (pos + n >= (1LL << 31)) return false;
+    rb.diag_off = pos;
+    rb.val.assign((size_t)pos + (size_t)n, skip);    // bridged gaps keep the marker
+    std::copy(diag, diag + n, rb.val.begin() + pos);
+  }
+  // pass 2: values (the scan is deterministic: same runs, same numbering) and the mirrored slices
+  struct Upper { int tb; Seg s; };
+  std::vector<Upper> upper;
+  std::vector<int> entry_seg;
+  for (int b = 0; b < nb; b++) {
+    const int r0 = b * kThreads, r1 = std::min(n, r0 + kThreads);
+    scan_block(ind, col, nullptr, 0, r0, r1, bridge, segs, &entry_seg);
+    std::vector<LSeg> &ls = lower[(size_t)b];
+    for (LSeg &l : ls) {
+      const GRun &g = gruns[(size_t)l.grun];
+      l.s.kpos = (int)(g.pos + (r0 + l.s.t0 - g.row0));
     }
     const int k0 = ind[r0];
     for (int r = r0; r < r1; r++)
       for (int k = ind[r]; k < ind[r + 1]; k++) {
-        const Seg &s = segs[(size_t)entry_seg[(size_t)(k - k0)]];
-        rb.val[(size_t)s.kpos + (size_t)(r - r0 - s.t0)] = val[k];
+        const Seg &sg = ls[(size_t)entry_seg[(size_t)(k - k0)]].s;
+        rb.val[(size_t)sg.kpos + (size_t)(r - r0 - sg.t0)] = val[k];
       }
+    std::sort(ls.begin(), ls.end(), [](const LSeg &a, const LSeg &c) { return by_key_then_row(a.s, c.s); });
+  }
+  for (const GRun &g : gruns) {
+    // entry (i, j) adds val * x[i] to y[j]: rows i0 .. i0+len-1 of the run are the columns of the
+    // target rows j0 .. j0+len-1, j0 = i0 + key (a bridged gap travels along: both uses skip it)
+    int i0 = g.row0, j0 = g.row0 + g.key, left = g.len;
+    long long kp = g.pos;
+    while (left > 0) {
+      const int tb = j0 / kThreads, tt = j0 % kThreads;
+      const int piece = std::min(left, kThreads - tt);
+      upper.push_back(Upper{tb, Seg{-g.key, tt, piece, i0, (int)kp}});
+      i0 += piece; j0 += piece; kp += piece; left -= piece;
+    }
   }
   long long nseg = (long long)upper.size() * 2 + nb;
   if (!force && nnz > 0 && nseg * 16 > 2 * nnz + n) return false;
@@ -338,16 +434,42 @@ static bool build_sss_runs(int n, const int *ind, const int *col, const double *
     for (const Upper &u : upper) usorted[(size_t)fill[(size_t)u.tb]++] = u.s;
   }
   rb.blk.resize(4 * (size_t)nb);
+  rb.seg.clear();
+  *over_budget = 0;
   for (int b = 0; b < nb; b++) {
     const int r0 = b * kThreads, r1 = std::min(n, r0 + kThreads);
     std::sort(usorted.begin() + start[(size_t)b], usorted.begin() + start[(size_t)b + 1], by_key_then_row);
     rb.blk[4 * (size_t)b] = r0; rb.blk[4 * (size_t)b + 1] = r1 - r0;
     rb.blk[4 * (size_t)b + 2] = (int)(rb.seg.size() / 4);
     auto emit = [&](const Seg &s) { rb.seg.push_back(s.kpos); rb.seg.push_back(s.x0); rb.seg.push_back(s.t0); rb.seg.push_back(s.len); };
-    for (const Seg &s : lower[(size_t)b]) emit(s);
-    emit(Seg{0, 0, r1 - r0, r0, (int)(nnz + r0)});                    // the diagonal
+    for (const LSeg &l : lower[(size_t)b]) emit(l.s);
+    emit(Seg{0, 0, r1 - r0, r0, (int)(rb.diag_off + r0)});            // the diagonal
     for (int i = start[(size_t)b]; i < start[(size_t)b + 1]; i++) emit(usorted[(size_t)i]);
     rb.blk[4 * (size_t)b + 3] = (int)(rb.seg.size() / 4);
+    if (rb.blk[4 * (size_t)b + 3] - rb.blk[4 * (size_t)b + 2] > kRunBatch) (*over_budget)++;
+  }
+  flag_gap_blocks(rb);
+  return true;
+}
+
+// Block-major values stream best (one contiguous region per block: 256^3 SSS product 186 us
+// against 199 us global-run-major) as long as the blocks stay within one batch of descriptors;
+// when the grid lines do not line up with the blocks (384^3: 9-10 descriptors, 804 us) the
+// global-run-major layout brings them back to 7 (675 us).
+static bool build_sss_runs(int n, const int *ind, const int *col, const double *val, const double *diag, bool force,
+                           RunBuild &rb) {
+  const long long nnz = ind[n];
+  if (n == 0) return false;
+  if (nnz > 0 && !force && !sample_accepts(n, ind, col, nullptr, 0)) return false;
+  if (nnz + n >= (1LL << 31) - (nnz >> 6)) return false;
+  const int nb = (n + kThreads - 1) / kThreads;
+  long long over = 0;
+  if (!build_sss_runs_layout(n, ind, col, val, diag, force, false, rb, &over)) return false;
+  if (over * 8 <= nb) return true;
+  RunBuild alt;
+  long long over_alt = 0;
+  if (build_sss_runs_layout(n, ind, col, val, diag, force, true, alt, &over_alt) && over_alt < over) {
+    rb.blk.swap(alt.blk); rb.seg.swap(alt.seg); rb.val.swap(alt.val); rb.diag_off = alt.diag_off;
   }
   return true;
 }
@@ -360,7 +482,7 @@ int runs_try_sss(psp_mat *A, const int *ind, const int *col, const double *val, 
   RunBuild rb;
   if (!build_sss_runs(A->n, ind, col, val, diag, c.spmv_format > 0, rb)) return PSP_OK;
   PSP_TRY(upload_runs(A, rb, -1));
-  A->d_diag = A->d_rval + ind[A->n];    // the SSOR sweeps read the diagonal from here
+  A->d_diag = A->d_rval + rb.diag_off;  // the SSOR sweeps read the diagonal from here
   *accepted = true;
   return PSP_OK;
 }
@@ -372,17 +494,20 @@ int runs_to_csr(const psp_mat *A, std::vector<int> &ind, std::vector<int> &col, 
   PSP_CUDA(cudaMemcpy(blk.data(), A->d_rblk, sizeof(int) * blk.size(), cudaMemcpyDeviceToHost));
   PSP_CUDA(cudaMemcpy(seg.data(), A->d_rseg, sizeof(int) * seg.size(), cudaMemcpyDeviceToHost));
   PSP_CUDA(cudaMemcpy(rv.data(), A->d_rval, sizeof(double) * rv.size(), cudaMemcpyDeviceToHost));
+  for (int b = 0; b < A->nb; b++) blk[4 * (size_t)b + 1] &= ~kRunGapFlag;
   const int m = A->m;
   ind.assign((size_t)m + 1, 0);
   for (int b = 0; b < A->nb; b++)
     for (int s = blk[4 * (size_t)b + 2]; s < blk[4 * (size_t)b + 3]; s++)
-      for (int u = 0; u < seg[4 * (size_t)s + 3]; u++) ind[(size_t)(blk[4 * (size_t)b] + seg[4 * (size_t)s + 2] + u) + 1]++;
+      for (int u = 0; u < seg[4 * (size_t)s + 3]; u++)
+        if (!run_skip(rv[(size_t)seg[4 * (size_t)s] + (size_t)u])) ind[(size_t)(blk[4 * (size_t)b] + seg[4 * (size_t)s + 2] + u) + 1]++;
   for (int r = 0; r < m; r++) ind[(size_t)r + 1] += ind[(size_t)r];
   col.resize((size_t)ind[(size_t)m]); val.resize((size_t)ind[(size_t)m]);
   std::vector<int> fill(ind.begin(), ind.end() - 1);
   for (int b = 0; b < A->nb; b++)                   // runs of a block are in ascending-column order per row
     for (int s = blk[4 * (size_t)b + 2]; s < blk[4 * (size_t)b + 3]; s++)
       for (int u = 0; u < seg[4 * (size_t)s + 3]; u++) {
+        if (run_skip(rv[(size_t)seg[4 * (size_t)s] + (size_t)u])) continue;       // bridged gap
         const int r = blk[4 * (size_t)b] + seg[4 * (size_t)s + 2] + u;
         const int p = fill[(size_t)r]++;
         col[(size_t)p] = seg[4 * (size_t)s + 1] + u;
@@ -409,6 +534,7 @@ extern "C" int psp_runs_analyze(int sss, int m, const int *ind, const int *col, 
   *rval = (double *)malloc(sizeof(double) * (rb.val.size() + 1));
   if (!*blk || !*seg || !*rval) { free(*blk); free(*seg); free(*rval); set_error("psp_runs_analyze: out of memory"); return PSP_ERR_NOMEM; }
   memcpy(*blk, rb.blk.data(), sizeof(int) * rb.blk.size());
+  for (size_t b = 0; b < rb.blk.size() / 4; b++) (*blk)[4 * b + 1] &= ~kRunGapFlag;       // callers see the row count
   memcpy(*seg, rb.seg.data(), sizeof(int) * rb.seg.size());
   memcpy(*rval, rb.val.data(), sizeof(double) * rb.val.size());
   return PSP_OK;

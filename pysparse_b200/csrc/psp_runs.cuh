@@ -25,9 +25,30 @@
 // bit-identical to csr_matvec_kernel (csr_mat.c:49-54); for SSS the order is lower entries,
 // diagonal, upper entries ascending -- the order in which sss_matvec builds y[i].
 #pragma once
+#include <cstring>
+#include <type_traits>
 #include "psp_common.cuh"
 
 namespace psp {
+
+// A run may bridge a short gap (a row that has no entry on the run's diagonal: the first node of
+// every grid line on the -1 diagonal of a stencil matrix): the gap's slot of the value array holds
+// this quiet-NaN pattern and the kernel skips it -- without it every such gap would split the
+// run and a 256-row block of a 384-wide grid would need 9-10 descriptors instead of 7, i.e. two
+// batches (two memory round trips) instead of one.  The analysis does not bridge when a stored
+// value of the matrix has exactly this bit pattern.
+constexpr unsigned long long kRunSkip = 0xFFF8C0DE5EED0002ull;
+constexpr int kRunGapMax = 2;             // rows a run may bridge
+constexpr int kRunGapFlag = 1 << 30;      // in a block descriptor's row count: some run of the block covers a gap
+constexpr int kRunBatch = 8;              // descriptors per batch of loads in run_pass (its UNROLL)
+constexpr int kRunGapMinLen = 16;         // ... once it is at least this long
+__host__ __device__ __forceinline__ bool run_skip(double v) {
+#ifdef __CUDA_ARCH__
+  return (unsigned long long)__double_as_longlong(v) == kRunSkip;
+#else
+  unsigned long long b; memcpy(&b, &v, 8); return b == kRunSkip;
+#endif
+}
 
 struct RunView {
   const double *val;        // run-ordered values (SSS: strict lower triangle, then the diagonal)
@@ -110,6 +131,8 @@ __device__ __forceinline__ void run_pass(const RunView &A, const double *x, RunS
       const int b = b0 + jb;
       if (b >= A.nint && (PER_BLOCK || !halo_ready)) { haloop(b); halo_ready = true; }
       const int4 d = sb[jb];
+      const bool gaps = (d.y & kRunGapFlag) != 0;
+      const int nrows = d.y & ~kRunGapFlag;
       const int o = d.z - sbase, ns = d.w - d.z;       // this block's runs: cache positions o .. o+ns-1
       double sum = 0.0;
       if (o + ns <= kRunSegCache) {
@@ -119,28 +142,37 @@ __device__ __forceinline__ void run_pass(const RunView &A, const double *x, RunS
         // on a scoreboard it shares with them -- one DRAM round trip per run instead of per batch.
         // (ptxas still forms the first product before the last loads are issued; forcing all
         // loads first through an artificial data dependency measured slower, profiles/r2_runs_notes.md.)
-        for (int s = 0; s < ns; s += UNROLL) {
-          unsigned iv[UNROLL], ix[UNROLL];
-          bool in[UNROLL];
-          double v[UNROLL], xv[UNROLL];
+        // GAPS: some run of this block bridges a gap -- only then are the loaded values tested for
+        // the marker (the test costs two instructions per run in an issue-bound loop: 3 % at 256^3)
+        auto batches = [&](auto GAPS) {
+          for (int s = 0; s < ns; s += UNROLL) {
+            unsigned iv[UNROLL], ix[UNROLL];
+            bool in[UNROLL];
+            double v[UNROLL], xv[UNROLL];
 #pragma unroll
-          for (int j = 0; j < UNROLL; j++) {
-            const int i = s + j;
-            const int4 g = sg[o + (i < ns ? i : 0)];
-            const unsigned u = (unsigned)(t - g.z);
-            in[j] = (i < ns) && u < (unsigned)g.w;
-            iv[j] = (unsigned)g.x + u;
-            ix[j] = (unsigned)g.y + u;
+            for (int j = 0; j < UNROLL; j++) {
+              const int i = s + j;
+              const int4 g = sg[o + (i < ns ? i : 0)];
+              const unsigned u = (unsigned)(t - g.z);
+              in[j] = (i < ns) && u < (unsigned)g.w;
+              iv[j] = (unsigned)g.x + u;
+              ix[j] = (unsigned)g.y + u;
+            }
+#pragma unroll
+            for (int j = 0; j < UNROLL; j++) {
+              v[j] = in[j] ? __ldg(A.val + iv[j]) : 0.0;
+              xv[j] = in[j] ? (NC ? __ldg(x + ix[j]) : x[ix[j]]) : 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < UNROLL; j++) {           // conditional: adding a zero product would turn -0.0 into +0.0
+              bool use = in[j];
+              if (decltype(GAPS)::value) use = use && !run_skip(v[j]);
+              if (use) sum = __dadd_rn(sum, __dmul_rn(v[j], xv[j]));
+            }
           }
-#pragma unroll
-          for (int j = 0; j < UNROLL; j++) {
-            v[j] = in[j] ? __ldg(A.val + iv[j]) : 0.0;
-            xv[j] = in[j] ? (NC ? __ldg(x + ix[j]) : x[ix[j]]) : 0.0;
-          }
-#pragma unroll
-          for (int j = 0; j < UNROLL; j++)             // conditional: adding a zero product would turn -0.0 into +0.0
-            if (in[j]) sum = __dadd_rn(sum, __dmul_rn(v[j], xv[j]));
-        }
+        };
+        if (gaps) batches(std::true_type());
+        else batches(std::false_type());
       } else {
         // more runs than the cache holds (irregular block): descriptors straight from global memory
         for (int i = 0; i < ns; i++) {
@@ -148,11 +180,12 @@ __device__ __forceinline__ void run_pass(const RunView &A, const double *x, RunS
           const unsigned u = (unsigned)(t - g.z);
           if (u < (unsigned)g.w) {
             const double *xp = x + (size_t)(unsigned)g.y + u;
-            sum = __dadd_rn(sum, __dmul_rn(__ldg(A.val + (size_t)(unsigned)g.x + u), NC ? __ldg(xp) : *xp));
+            const double av = __ldg(A.val + (size_t)(unsigned)g.x + u);
+            if (!run_skip(av)) sum = __dadd_rn(sum, __dmul_rn(av, NC ? __ldg(xp) : *xp));
           }
         }
       }
-      if (t < d.y) rowop(d.x + t, sum);
+      if (t < nrows) rowop(d.x + t, sum);
     }
     cp_async_wait_all();
     __syncthreads();

@@ -178,8 +178,11 @@ __global__ void __launch_bounds__(kThreads, 4) k_spmv_stream(SpmvArgs a) {
 // lines per warp instruction instead of one line per diagonal per few lanes.
 // The pass itself lives in psp_tma_ring.cuh (shared with the persistent solver
 // kernels).
+// (shared memory admits at most 4 CTAs per SM -- 2 stages of 25.7 KB each -- so 64 registers per
+// thread cost no occupancy; with the default bound ptxas aims at 8 CTAs, stops at 32 registers and
+// spills the two running dot products around the irregular-row phase)
 template <int STAGES, bool DOTS>
-__global__ void __launch_bounds__(kThreads) k_spmv_tma(SpmvArgs a) {
+__global__ void __launch_bounds__(kThreads, 4) k_spmv_tma(SpmvArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t full[STAGES];
   __shared__ double red_sh[8];

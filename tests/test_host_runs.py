@@ -35,14 +35,29 @@ def analyze(native, sss, m, ind, col, val, diag=None):
     return out
 
 
+SKIP = np.array([0xFFF8C0DE5EED0002], dtype=np.uint64).view(np.float64)[0]     # kRunSkip of psp_runs.cuh
+
+
+def is_skip(v):
+    return np.array([v], dtype=np.float64).view(np.uint64)[0] == 0xFFF8C0DE5EED0002
+
+
+def n_skips(rval):
+    return int((np.asarray(rval).view(np.uint64) == 0xFFF8C0DE5EED0002).sum())
+
+
 def rebuild_rows(m, blk, seg, rval):
-    """rows[r] = [(col, val), ...] in the order the kernel adds them"""
+    """rows[r] = [(col, val), ...] in the order the kernel adds them (the marker in a bridged gap
+    of a run is what the kernel skips)"""
     rows = [[] for _ in range(m)]
+    skip = np.asarray(rval).view(np.uint64) == 0xFFF8C0DE5EED0002
     for r0, nrows, s0, s1 in blk:
         for kpos, x0, t0, ln in seg[s0:s1]:
             assert 0 <= t0 and t0 + ln <= nrows and ln > 0
+            assert not skip[kpos] and not skip[kpos + ln - 1]          # a gap is strictly inside its run
             for u in range(ln):
-                rows[r0 + t0 + u].append((x0 + u, rval[kpos + u]))
+                if not skip[kpos + u]:
+                    rows[r0 + t0 + u].append((x0 + u, rval[kpos + u]))
     return rows
 
 
@@ -54,7 +69,7 @@ def test_csr_runs_rebuild_the_matrix_in_row_order(native, spec):
     m = len(ind) - 1
     blk, seg, rval = analyze(native, False, m, ind, col, val)
     assert np.array_equal(blk[:, 0], np.arange(0, m, 256)) and blk[:, 1].sum() == m
-    assert len(rval) == len(val)                                    # every value stored exactly once
+    assert len(rval) - n_skips(rval) == len(val)                    # every value stored exactly once
     rows = rebuild_rows(m, blk, seg, rval)
     for r in range(m):
         want = list(zip(col[ind[r]:ind[r + 1]].tolist(), val[ind[r]:ind[r + 1]].tolist()))
@@ -73,7 +88,7 @@ def test_sss_runs_store_each_value_once_and_keep_the_sss_order(native, spec):
     val, diag, col, ind = mat["sss"]
     n = len(diag)
     blk, seg, rval = analyze(native, True, n, ind, col, val, diag)
-    assert len(rval) == len(val) + n
+    assert len(rval) - n_skips(rval) == len(val) + n
     rows = rebuild_rows(n, blk, seg, rval)
     upper = [[] for _ in range(n)]
     for i in range(n):
@@ -82,3 +97,38 @@ def test_sss_runs_store_each_value_once_and_keep_the_sss_order(native, spec):
     for r in range(n):
         want = list(zip(col[ind[r]:ind[r + 1]].tolist(), val[ind[r]:ind[r + 1]].tolist())) + [(r, diag[r])] + upper[r]
         assert rows[r] == want, r
+
+
+def test_runs_bridge_the_one_row_gaps_of_grid_lines(native):
+    """The -1 / +1 diagonals of a grid matrix have no entry at the first / last node of every grid
+    line.  The analysis bridges such a gap with a marker value instead of ending the run there, so a
+    block needs one descriptor per diagonal (one batch of loads in the kernel) however the lines
+    fall into the 256-row blocks; a value that looks like the marker switches bridging off."""
+    from pysparse_b200.tools import gallery as g
+    mat = g.poisson2d(96)                                            # lines of 96 rows: 2 2/3 lines per block
+    val, col, ind = mat["csr"]
+    m = mat["n"]
+    blk, seg, rval = analyze(native, False, m, ind, col, val)
+    per_block = blk[:, 3] - blk[:, 2]
+    assert n_skips(rval) > 0 and per_block.max() <= 7               # 5 diagonals; +-96 start / stop inside edge blocks
+    interior = per_block[2:-2]
+    assert (interior == 5).all()
+    rows = rebuild_rows(m, blk, seg, rval)
+    for r in range(0, m, 37):
+        assert rows[r] == list(zip(col[ind[r]:ind[r + 1]].tolist(), val[ind[r]:ind[r + 1]].tolist()))
+    # the same structure with a stored value equal to the marker: no bridging, nothing is skipped
+    val2 = val.copy(); val2[5] = SKIP
+    blk2, seg2, rval2 = analyze(native, False, m, ind, col, val2)
+    assert len(rval2) == len(val2) and len(seg2) > len(seg)
+    # symmetric form: lower runs bridge, the mirrored runs inherit the gaps
+    sval, sdiag, scol, sind = mat["sss"]
+    blk3, seg3, rval3 = analyze(native, True, m, sind, scol, sval, sdiag)
+    assert n_skips(rval3) > 0 and (blk3[:, 3] - blk3[:, 2] <= 8).all()       # one batch of descriptors per block
+    # 3-D: block-major storage would need 3 lower + diagonal + up to 6 mirrored slices per block; the
+    # analysis then stores the values global-run-major and the interior blocks are back to 7
+    mat = g.poisson3d(96, want_csr=False)
+    sval, sdiag, scol, sind = mat["sss"]
+    blk4, seg4, rval4 = analyze(native, True, mat["n"], sind, scol, sval, sdiag)
+    per = blk4[:, 3] - blk4[:, 2]
+    assert np.median(per) == 7 and per.max() <= 8
+    assert len(rval4) - n_skips(rval4) == len(sval) + mat["n"]
