@@ -50,7 +50,8 @@ print(f"spmv sss poisson3d {g}^3: {dt * 1e6:.0f} us, {nb / dt / 1e9:.0f} GB/s al
       f"{2 * (2 * nnz + n) / dt / 1e9:.0f} GFLOP/s", flush=True)
 # spot check against the stencil itself: y = A x at a few interior rows
 y = dy.download(); x = dx.download()
-for r in (g * g * 5 + g * 7 + 9, n // 2 + 3, n - g * g - g - 2):
+for z, yy, xx in ((5, 7, 9), (g // 2, g // 2, 3), (g - 2, g - 2, g - 2)):          # interior nodes
+    r = (z * g + yy) * g + xx
     ref = 6.0 * x[r] - x[r - 1] - x[r + 1] - x[r - g] - x[r + g] - x[r - g * g] - x[r + g * g]
     assert abs(y[r] - ref) <= 1e-12 * max(1.0, abs(ref)), (r, y[r], ref)
 print("spot check ok", flush=True)
