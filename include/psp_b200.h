@@ -88,7 +88,8 @@ int psp_matvec(psp_mat *a, int transp, const double *x, long incx, double *y, lo
  * rows of csr_matvec_kernel / sss_matvec re-expressed as runs of consecutive rows on one diagonal.
  * sss = 0: CSR arrays (diag ignored); sss = 1: strict lower triangle + diagonal, every stored
  * value kept once and referenced by two run descriptors.  Outputs (malloc'ed, release with
- * psp_runs_free): blk[4 nblk] = (first row, rows, first run, end run), seg[4 nseg] = (position of
+ * psp_runs_free): blk[4 nblk] = (first row, rows | 1<<30 when a run of the block covers a bridged gap,
+ * first run, end run), seg[4 nseg] = (position of
  * the first value, first column, first local row, length), rval[nval].  Bit-exact structure
  * work; needs no GPU (the CPU tests rebuild the matrix from it). */
 int psp_runs_analyze(int sss, int m, const int *ind, const int *col, const double *val, const double *diag,

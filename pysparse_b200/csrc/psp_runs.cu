@@ -260,7 +260,9 @@ static void flag_gap_blocks(RunBuild &rb) {
     bool gap = false;
     for (int sgi = rb.blk[4 * b + 2]; sgi < rb.blk[4 * b + 3] && !gap; sgi++) {
       const size_t k0 = (size_t)rb.seg[4 * (size_t)sgi], len = (size_t)rb.seg[4 * (size_t)sgi + 3];
-      for (size_t u = 1; u + 1 < len; u++)           // a gap is strictly inside its run
+      // (a lower run never starts or ends on a gap, but a mirrored slice of it can: the slices are
+      // cut at the target block's boundaries)
+      for (size_t u = 0; u < len; u++)
         if (bits[k0 + u] == kRunSkip) { gap = true; break; }
     }
     if (gap) rb.blk[4 * b + 1] |= kRunGapFlag;
@@ -534,7 +536,6 @@ extern "C" int psp_runs_analyze(int sss, int m, const int *ind, const int *col, 
   *rval = (double *)malloc(sizeof(double) * (rb.val.size() + 1));
   if (!*blk || !*seg || !*rval) { free(*blk); free(*seg); free(*rval); set_error("psp_runs_analyze: out of memory"); return PSP_ERR_NOMEM; }
   memcpy(*blk, rb.blk.data(), sizeof(int) * rb.blk.size());
-  for (size_t b = 0; b < rb.blk.size() / 4; b++) (*blk)[4 * b + 1] &= ~kRunGapFlag;       // callers see the row count
   memcpy(*seg, rb.seg.data(), sizeof(int) * rb.seg.size());
   memcpy(*rval, rb.val.data(), sizeof(double) * rb.val.size());
   return PSP_OK;

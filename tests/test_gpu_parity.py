@@ -380,3 +380,38 @@ def test_sharded_solvers_two_gpus(native):
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(root, "scripts", "dist_check.py")]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0 and "DIST CHECK PASSED" in p.stdout, p.stdout[-3000:] + p.stderr[-2000:]
+
+
+@pytest.mark.parametrize("grid", [96, 384, 200])
+def test_run_format_bridged_gaps_on_unaligned_grids_vs_oracle(gpu, native, checker, grid):
+    """Grids whose lines do not line up with the 256-row blocks (2-D Poisson, lines of 96 / 384 / 200
+    rows), run format forced.  The -1 / +1 runs bridge the missing entry at every line start with a
+    marker value; the mirrored slices of the symmetric form are cut at the target blocks' boundaries
+    and may therefore START or END on such a marker (lines of 384: row 768 = 3 * 256) -- every block in
+    reach of one must skip it.  Products, transposed products and a PCG solve against the reference's
+    kernels, bit for bit."""
+    from pysparse_b200.tools import gallery
+    native.set_option("spmv_format", 1)
+    try:
+        mat = gallery.poisson2d(grid)
+        n = mat["n"]
+        x = np.random.default_rng(grid).standard_normal(n)
+        A = gpu.csr(n, n, *mat["csr"]); S = gpu.sss(n, *mat["sss"])
+        Ao = checker.csr(n, n, *mat["csr"]); So = checker.sss(n, *mat["sss"])
+        y = np.full(n, np.nan); gpu.matvec(A, x, y)
+        yo = np.zeros(n); checker.matvec(Ao, x, yo)
+        assert np.array_equal(y, yo)
+        yt = np.full(n, np.nan); gpu.matvec(A, x, yt, transp=True)
+        yto = np.zeros(n); checker.matvec(Ao, x, yto, transp=True)
+        assert np.array_equal(yt, yto)
+        ys = np.full(n, np.nan); gpu.matvec(S, x, ys)
+        yso = np.zeros(n); checker.matvec(So, x, yso)
+        assert np.array_equal(ys, yso)
+        b = np.ones(n); xs = np.zeros(n); xso = np.zeros(n)
+        K = gpu.jacobi(S, mat["sss"][1], 1.0, 1); Ko = checker.jacobi(So, mat["sss"][1])
+        r = gpu.solve("pcg", S, b, xs, 1e-8, 60, K)
+        ro = checker.solve("pcg", So, b, xso, 1e-8, 60, Ko)
+        assert r[:2] == ro[:2] and abs(r[2] - ro[2]) <= 1e-6 * abs(ro[2])
+        assert np.max(np.abs(xs - xso)) <= 1e-9 * np.max(np.abs(xso))
+    finally:
+        native.set_option("spmv_format", -1)
