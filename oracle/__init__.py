@@ -228,3 +228,65 @@ class Oracle:
         if rc == -100:
             raise ValueError(solver)
         return info.value, it.value, rr.value
+
+
+class RefCorrEq:
+    """The reference's own JDSYM correction-equation operator (``pysparse/eigen/src/correq.c``,
+    compiled into ``oracle/_ref``): ``update(k, theta, H)``, ``right(r)`` (in place),
+    ``matvec(x, y)``, ``precon(x, y)``.  ``A``, ``M``, ``K`` are operator handles of the same
+    ``Oracle("ref")``; ``Q``, ``Qm``, ``Y`` are n x kmax Fortran-ordered arrays that the operator
+    borrows (the caller keeps writing into them, as jdsym.c does); ``H`` is kmax x kmax."""
+
+    def __init__(self, ora: Oracle, optype, n, A: Handle, M: Handle | None, K: Handle | None, Q, Qm, Y, kmax):
+        assert ora.which == "ref", "only the compiled reference has a correction equation"
+        L = ora.lib
+        if not hasattr(L, "ref_correq_new"):
+            raise RuntimeError("oracle/_ref was built without correq.c (rebuild: make -C oracle ref)")
+        for a in (Q, Qm, Y):
+            assert a is None or (a.dtype == np.float64 and a.flags.f_contiguous and a.shape == (n, kmax))
+        self._lib, self.n, self.kmax = L, n, kmax
+        self._keep = (A, M, K, Q, Qm, Y)
+        L.ref_correq_new.restype = C.c_void_p
+        L.ref_correq_new.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, _dp, _dp, _dp, C.c_int]
+        L.ref_correq_update.argtypes = [C.c_void_p, C.c_int, C.c_double, _dp]
+        L.ref_correq_update.restype = C.c_int
+        for name in ("ref_correq_matvec", "ref_correq_precon"):
+            getattr(L, name).argtypes = [C.c_void_p, _dp, _dp]
+            getattr(L, name).restype = None
+        L.ref_correq_right.argtypes = [C.c_void_p, _dp]
+        L.ref_correq_right.restype = None
+        L.ref_correq_free.argtypes = [C.c_void_p]
+        L.ref_correq_free.restype = None
+        self.ptr = L.ref_correq_new(optype, n, A.ptr, M.ptr if M is not None else None, K.ptr if K is not None else None,
+                                    _p(Q), _p(Qm) if Qm is not None else None, _p(Y) if Y is not None else None, kmax)
+
+    def update(self, k, theta, H=None):
+        Hf = None
+        if H is not None:
+            Hf = np.asfortranarray(H, dtype=np.float64)
+            assert Hf.shape == (self.kmax, self.kmax)
+        info = self._lib.ref_correq_update(self.ptr, k, theta, _p(Hf) if Hf is not None else None)
+        if info:
+            raise ValueError("H is singular")
+
+    def right(self, r):
+        assert r.dtype == np.float64 and r.flags.c_contiguous
+        self._lib.ref_correq_right(self.ptr, _p(r))
+
+    def matvec(self, x, y):
+        x = _f64(x)
+        assert y.dtype == np.float64 and y.flags.c_contiguous
+        self._lib.ref_correq_matvec(self.ptr, _p(x), _p(y))
+
+    def precon(self, x, y):
+        x = _f64(x)
+        assert y.dtype == np.float64 and y.flags.c_contiguous
+        self._lib.ref_correq_precon(self.ptr, _p(x), _p(y))
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self._lib.ref_correq_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass

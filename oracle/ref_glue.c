@@ -18,6 +18,9 @@
  *         pysparse/sparse/src/sss_mat.c:40-76          (sss matvec)
  *         pysparse/precon/src/preconmodule.c:35-54     (jacobi)
  *         pysparse/precon/src/preconmodule.c:95-193    (ssor / symgs)
+ *         pysparse/eigen/src/correq.c:1-236            (JDSYM correction-equation operator:
+ *                                                       object layout, projections, right / matvec / precon)
+ *         pysparse/eigen/src/orthopack.c:124-135       (mgs, which CorrEq_right calls)
  *     are extracted with `sed -n` into a scratch directory at build time and
  *     #included below (REF_*_INC).  No reference text is stored in this repo.
  *
@@ -336,6 +339,142 @@ int ref_solve(int solver, void *A, void *K, int n, double *b, double *x,
   free(work);
   return rc;
 }
+
+/* ------------------------------------------------------------------ */
+/* JDSYM correction equation: pysparse/eigen/src/correq.c as it is      */
+/* ------------------------------------------------------------------ */
+#ifdef REF_CORREQ_INC
+#include <assert.h>
+/* what jdsymmodule.c:27-31 defines before it #includes correq.c */
+static int ONE = 1;
+static double DONE = 1.0, DZER = 0.0, DMONE = -1.0;
+
+/* BLAS-2 / LAPACK pieces correq.c expects from the external Fortran libraries: Netlib reference
+ * semantics (column-major, unblocked), only the cases correq.c / jdsym.c:533-537 use */
+void F77(dgemv)(char *trans, int *m, int *n, double *alpha, double *a, int *lda, double *x, int *incx,
+                double *beta, double *y, int *incy, int ltrans)
+{
+  int i, j;
+  (void)incx; (void)incy; (void)ltrans;               /* always 1 here */
+  if (*trans == 't' || *trans == 'T') {
+    for (j = 0; j < *n; j++) {
+      double t = 0.0;
+      for (i = 0; i < *m; i++) t = t + a[(size_t)j * *lda + i] * x[i];
+      y[j] = (*beta == 0.0) ? *alpha * t : *alpha * t + *beta * y[j];
+    }
+  } else {
+    if (*beta == 0.0) for (i = 0; i < *m; i++) y[i] = 0.0;
+    else if (*beta != 1.0) for (i = 0; i < *m; i++) y[i] = *beta * y[i];
+    for (j = 0; j < *n; j++) {
+      double t = *alpha * x[j];
+      if (t != 0.0)
+        for (i = 0; i < *m; i++) y[i] = y[i] + t * a[(size_t)j * *lda + i];
+    }
+  }
+}
+
+static void glue_dgetf2(int n, double *a, int lda, int *ipiv, int *info)
+{
+  int i, j, c;
+  *info = 0;
+  for (j = 0; j < n; j++) {
+    int p = j;
+    for (i = j + 1; i < n; i++)
+      if (fabs(a[(size_t)j * lda + i]) > fabs(a[(size_t)j * lda + p])) p = i;
+    ipiv[j] = p + 1;
+    if (a[(size_t)j * lda + p] == 0.0) { if (!*info) *info = j + 1; continue; }
+    if (p != j)
+      for (c = 0; c < n; c++) { double t = a[(size_t)c * lda + j]; a[(size_t)c * lda + j] = a[(size_t)c * lda + p]; a[(size_t)c * lda + p] = t; }
+    { double r = 1.0 / a[(size_t)j * lda + j]; for (i = j + 1; i < n; i++) a[(size_t)j * lda + i] = a[(size_t)j * lda + i] * r; }
+    for (c = j + 1; c < n; c++) {
+      double t = a[(size_t)c * lda + j];
+      for (i = j + 1; i < n; i++) a[(size_t)c * lda + i] = a[(size_t)c * lda + i] - a[(size_t)j * lda + i] * t;
+    }
+  }
+}
+
+void F77(dgetrs)(char *trans, int *n, int *nrhs, double *a, int *lda, int *ipiv, double *b, int *ldb, int *info, int ltrans)
+{
+  int i, j;
+  (void)trans; (void)nrhs; (void)ldb; (void)ltrans;   /* "n", one right-hand side */
+  *info = 0;
+  for (i = 0; i < *n; i++) { int p = ipiv[i] - 1; if (p != i) { double t = b[i]; b[i] = b[p]; b[p] = t; } }
+  for (j = 0; j < *n; j++)                              /* L y = b, unit lower */
+    if (b[j] != 0.0)
+      for (i = j + 1; i < *n; i++) b[i] = b[i] - b[j] * a[(size_t)j * *lda + i];
+  for (j = *n - 1; j >= 0; j--)                         /* U x = y */
+    if (b[j] != 0.0) {
+      b[j] = b[j] / a[(size_t)j * *lda + j];
+      for (i = 0; i < j; i++) b[i] = b[i] - b[j] * a[(size_t)j * *lda + i];
+    }
+}
+
+/* the operator sees its vectors as NumPy arrays; only ->data is dereferenced */
+typedef struct { char *data; } PyArrayObject;
+#define SPMATRIX_PARSE_ARGS_ARR_ARR(args, xp, yp, n1, n2) \
+  do { xp = ((PyArrayObject **)(args))[0]; yp = ((PyArrayObject **)(args))[1]; } while (0)
+#define SpMatrix_Matvec glue_matvec
+#define SpMatrix_Precon glue_precon
+#include REF_MGS_INC
+#include REF_CORREQ_INC
+#undef SpMatrix_Matvec
+#undef SpMatrix_Precon
+
+typedef struct { CorrEqObject ce; double *H; int kmax; } ref_correq;
+
+/* newCorrEqObject (correq.c:307-341) + the work arrays jdsym.c:176-190 allocates around it */
+void *ref_correq_new(int optype, int n, void *amat, void *mmat, void *prec, double *Q, double *Qm, double *Y, int kmax)
+{
+  ref_correq *r = (ref_correq *)calloc(1, sizeof *r);
+  r->kmax = kmax;
+  r->ce.op_type = optype; r->ce.n = n;
+  r->ce.amat = (PyObject *)amat; r->ce.mmat = (PyObject *)mmat; r->ce.prec = (PyObject *)prec;
+  r->ce.Q = Q; r->ce.Qm = Qm; r->ce.Y = Y;
+  r->ce.Hlu = (double *)calloc((size_t)kmax * kmax, sizeof(double));
+  r->ce.Hpiv = (int *)calloc((size_t)kmax, sizeof(int));
+  r->ce.ldh = kmax;
+  r->ce.work = (double *)calloc(2 * (size_t)(n > 0 ? n : 1), sizeof(double));
+  r->ce.right = CorrEq_right; r->ce.update = CorrEq_update;
+  return r;
+}
+
+/* jdsym.c:533-537 (copy H, factor its leading k x k block) followed by CorrEq_update (:569);
+ * H: kmax x kmax, column-major, or NULL when there is no preconditioner */
+int ref_correq_update(void *h, int k, double theta, const double *H)
+{
+  ref_correq *r = (ref_correq *)h;
+  int info = 0;
+  if (H) {
+    memcpy(r->ce.Hlu, H, sizeof(double) * (size_t)r->kmax * r->kmax);
+    glue_dgetf2(k, r->ce.Hlu, r->kmax, r->ce.Hpiv, &info);
+  }
+  r->ce.update(&r->ce, k, theta);
+  return info;
+}
+
+void ref_correq_right(void *h, double *rhs) { ref_correq *r = (ref_correq *)h; r->ce.right(&r->ce, rhs); }
+
+void ref_correq_matvec(void *h, double *x, double *y)
+{
+  PyArrayObject xa = {(char *)x}, ya = {(char *)y};
+  PyArrayObject *args[2] = {&xa, &ya};
+  CorrEq_matvec(&((ref_correq *)h)->ce, (PyObject *)args);
+}
+
+void ref_correq_precon(void *h, double *x, double *y)
+{
+  PyArrayObject xa = {(char *)x}, ya = {(char *)y};
+  PyArrayObject *args[2] = {&xa, &ya};
+  CorrEq_precon(&((ref_correq *)h)->ce, (PyObject *)args);
+}
+
+void ref_correq_free(void *h)
+{
+  ref_correq *r = (ref_correq *)h;
+  if (!r) return;
+  free(r->ce.Hlu); free(r->ce.Hpiv); free(r->ce.work); free(r);
+}
+#endif  /* REF_CORREQ_INC */
 
 const char *ref_describe(void)
 {
